@@ -1,0 +1,221 @@
+// gs_raster.cu — one CTA per 16x16 tile: the reference's fragment shader (index.js:170-175) and its
+// blend state (index.js:177-181), composited front-to-back with transmittance.
+//
+// The tile's instance range [tile_start[t], tile_start[t+1]) holds 32 B projected records already laid
+// out contiguously in back-to-front draw order, so the kernel pulls them with 1-D TMA bulk copies
+// (cp.async.bulk.shared::cluster.global + mbarrier complete_tx) through a 4-stage shared-memory ring and
+// walks every chunk from its end (nearest splat) to its start.
+//
+//   back-to-front (reference):  C <- c*a + C*(1-a),  A <- a + A*(1-a)      (index.js:177-178)
+//   front-to-back (here):       C  = sum_i c_i a_i T_i + bg*T_end,  A = 1 - T_end + bg.a*T_end,
+//                               T_i = prod_{j nearer than i} (1 - a_j)      
+// The two are algebraically identical; a tile stops early once every pixel has T < 1e-4, which bounds the
+// dropped contribution by 1e-4 per channel (the parity tolerance is 1e-3).
+#include "gs_common.cuh"
+
+namespace gs {
+
+constexpr int kChunk = 128;   // records per TMA bulk copy (4 KB)
+constexpr int kStages = 4;    // ring depth
+constexpr float kTStop = 1e-4f;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+
+// index (within rank `rank`'s packed tile list) of tile (tx, ty); tiles are owned when (tx+ty)%world==rank
+__host__ __device__ inline uint32_t owned_in_row(uint32_t tiles_x, uint32_t ty, uint32_t upto_x, uint32_t rank,
+                                                 uint32_t world) {
+  // number of tx in [0, upto_x) with (tx + ty) % world == rank
+  const uint32_t r0 = (rank + world - (ty % world)) % world;
+  (void)tiles_x;
+  return upto_x > r0 ? (upto_x - 1 - r0) / world + 1 : 0u;
+}
+__host__ __device__ inline uint32_t owned_slot(uint32_t tx, uint32_t ty, uint32_t tiles_x, uint32_t rank,
+                                               uint32_t world) {
+  // every `world` consecutive rows own exactly tiles_x tiles between them
+  uint32_t slot = (ty / world) * tiles_x;
+  for (uint32_t y = (ty / world) * world; y < ty; ++y) slot += owned_in_row(tiles_x, y, tiles_x, rank, world);
+  return slot + owned_in_row(tiles_x, ty, tx, rank, world);
+}
+
+__device__ __forceinline__ uint32_t to_u8(float v) {
+  v = fminf(fmaxf(v, 0.0f), 1.0f);
+  return (uint32_t)(v * 255.0f + 0.5f);
+}
+
+__global__ void __launch_bounds__(256) k_raster(const float4 *__restrict__ inst_rec,
+                                                const uint32_t *__restrict__ tile_start, RenderConsts rc,
+                                                void *__restrict__ out) {
+  __shared__ __align__(128) float4 s_rec[kStages][kChunk * 2];
+  __shared__ __align__(16) float4 s_col[kChunk];
+  __shared__ __align__(8) uint64_t s_full[kStages];
+
+  const uint32_t tile = blockIdx.x;
+  const uint32_t tx = tile % rc.tiles_x, ty = tile / rc.tiles_x;
+  if (rc.shard_world > 1 && ((tx + ty) % rc.shard_world) != rc.shard_rank) return;
+
+  const uint32_t tid = threadIdx.x;
+  const uint32_t lx = tid & 15u, ly = tid >> 4;
+  const uint32_t x = tx * kTile + lx, y = ty * kTile + ly;
+  const bool inside = (x < rc.width) && (y < rc.height);
+  const float fx = (float)x + 0.5f, fy = (float)y + 0.5f;  // pixel centre, GL window coordinates
+
+  const uint32_t start = tile_start[tile], end = tile_start[tile + 1];
+  const uint32_t count = end - start;
+  const uint32_t n_chunks = (count + kChunk - 1) / kChunk;
+
+  if (tid == 0) {
+    for (int s = 0; s < kStages; ++s) mbar_init(&s_full[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  // chunk k covers records [lo_k, hi_k) with hi_k = end - k*kChunk (nearest first)
+  auto issue = [&](uint32_t k) {
+    const uint32_t hi = end - k * kChunk;
+    const uint32_t lo = (hi - start > (uint32_t)kChunk) ? hi - kChunk : start;
+    const uint32_t bytes = (hi - lo) * 32u;
+    uint64_t *bar = &s_full[k % kStages];
+    mbar_expect_tx(bar, bytes);
+    bulk_g2s(&s_rec[k % kStages][0], inst_rec + 2 * (size_t)lo, bytes, bar);
+  };
+  if (tid == 0) {
+    for (uint32_t k = 0; k < (uint32_t)kStages && k < n_chunks; ++k) issue(k);
+  }
+
+  float T = 1.0f, Cr = 0.0f, Cg = 0.0f, Cb = 0.0f;
+  uint32_t k = 0;
+  for (; k < n_chunks; ++k) {
+    const uint32_t stage = k % kStages;
+    mbar_wait(&s_full[stage], (k / kStages) & 1u);
+    const uint32_t hi = end - k * kChunk;
+    const uint32_t lo = (hi - start > (uint32_t)kChunk) ? hi - kChunk : start;
+    const uint32_t m = hi - lo;
+    const float4 *rec = &s_rec[stage][0];
+    // colour bytes -> float once per record (index.js:152-157), not once per pixel
+    if (tid < m) {
+      const float4 r1 = rec[2 * tid + 1];
+      const uint32_t bits = __float_as_uint(r1.z);
+      s_col[tid] = make_float4(__fdiv_rn((float)(bits & 255u), 255.0f), __fdiv_rn((float)((bits >> 8) & 255u), 255.0f),
+                               __fdiv_rn((float)((bits >> 16) & 255u), 255.0f), r1.w);
+    }
+    __syncthreads();
+    if (T >= kTStop) {
+      for (int j = (int)m - 1; j >= 0; --j) {
+        const float4 r0 = rec[2 * j];      // cx, cy, a1x, a1y
+        const float4 r1 = rec[2 * j + 1];  // a2x, a2y, rgba bits, alpha
+        const float dx = __fsub_rn(fx, r0.x), dy = __fsub_rn(fy, r0.y);
+        // vPosition = (px, py): same op order as the oracle (orc band_worker)
+        const float px = __fmaf_rn(dy, r1.y, __fmul_rn(dx, r1.x));
+        const float py = __fmaf_rn(dy, r0.w, __fmul_rn(dx, r0.z));
+        const float r2 = __fmaf_rn(py, py, __fmul_rn(px, px));
+        if (r2 <= 4.0f) {  // index.js:171-172: A = -r2; discard if A < -4
+          const float4 col = s_col[j];
+          const float alpha = __fmul_rn(__expf(-r2), col.w);  // index.js:173
+          const float w = __fmul_rn(alpha, T);
+          Cr = __fmaf_rn(col.x, w, Cr);
+          Cg = __fmaf_rn(col.y, w, Cg);
+          Cb = __fmaf_rn(col.z, w, Cb);
+          T = __fsub_rn(T, w);
+        }
+      }
+    }
+    const int alive = __syncthreads_or(inside && (T >= kTStop));
+    if (!alive) break;
+    if (tid == 0 && k + kStages < n_chunks) issue(k + kStages);
+  }
+  // early exit: bulk copies already in flight must land before the CTA (and its shared memory) retires
+  if (tid == 0 && k < n_chunks) {
+    for (uint32_t kk = k + 1; kk < n_chunks && kk < k + kStages; ++kk) mbar_wait(&s_full[kk % kStages], (kk / kStages) & 1u);
+  }
+
+  // composite over the clear colour
+  const float oR = __fmaf_rn(rc.bg[0], T, Cr), oG = __fmaf_rn(rc.bg[1], T, Cg), oB = __fmaf_rn(rc.bg[2], T, Cb);
+  const float oA = __fmaf_rn(rc.bg[3], T, 1.0f - T);
+  size_t pix;
+  bool write;
+  if (rc.out_tiled) {
+    const uint32_t slot =
+        (rc.shard_world > 1) ? owned_slot(tx, ty, rc.tiles_x, rc.shard_rank, rc.shard_world) : tile;
+    pix = (size_t)slot * 256 + tid;
+    write = true;
+  } else {
+    pix = (size_t)y * rc.width + x;
+    write = inside;
+  }
+  if (write) {
+    if (rc.out_format == GS_FORMAT_RGBA8) {
+      const uint32_t v = inside ? (to_u8(oR) | (to_u8(oG) << 8) | (to_u8(oB) << 16) | (to_u8(oA) << 24)) : 0u;
+      ((uint32_t *)out)[pix] = v;
+    } else {
+      ((float4 *)out)[pix] = inside ? make_float4(oR, oG, oB, oA) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+}
+
+// scatter `world` gathered tiled buffers back into a row-major frame (one thread per pixel)
+__global__ void __launch_bounds__(256) k_assemble(const void *__restrict__ gathered, uint32_t tiles_per_rank,
+                                                  uint32_t world, uint32_t width, uint32_t height, int32_t format,
+                                                  void *__restrict__ out) {
+  const uint32_t tiles_x = (width + kTile - 1) / kTile;
+  const uint32_t tile = blockIdx.x;
+  const uint32_t tx = tile % tiles_x, ty = tile / tiles_x;
+  const uint32_t tid = threadIdx.x;
+  const uint32_t x = tx * kTile + (tid & 15u), y = ty * kTile + (tid >> 4);
+  if (x >= width || y >= height) return;
+  const uint32_t rank = (tx + ty) % world;
+  const uint32_t slot = (world > 1) ? owned_slot(tx, ty, tiles_x, rank, world) : tile;
+  const size_t src = ((size_t)rank * tiles_per_rank + slot) * 256 + tid;
+  const size_t dst = (size_t)y * width + x;
+  if (format == GS_FORMAT_RGBA8) ((uint32_t *)out)[dst] = ((const uint32_t *)gathered)[src];
+  else ((float4 *)out)[dst] = ((const float4 *)gathered)[src];
+}
+
+void launch_raster(gs_context *c, const RenderConsts &rc, void *out_dev) {
+  k_raster<<<rc.n_tiles, 256, 0, c->stream>>>(c->inst_rec, c->tile_start, rc, out_dev);
+}
+
+void launch_assemble(gs_context *c, const void *gathered, uint32_t tiles_per_rank, uint32_t world, uint32_t width,
+                     uint32_t height, int32_t format, void *out_frame) {
+  const uint32_t tiles_x = (width + kTile - 1) / kTile, tiles_y = (height + kTile - 1) / kTile;
+  k_assemble<<<tiles_x * tiles_y, 256, 0, c->stream>>>(gathered, tiles_per_rank, world, width, height, format, out_frame);
+}
+
+uint32_t owned_tiles_host(uint32_t width, uint32_t height, uint32_t rank, uint32_t world) {
+  const uint32_t tiles_x = (width + kTile - 1) / kTile, tiles_y = (height + kTile - 1) / kTile;
+  if (world <= 1) return tiles_x * tiles_y;
+  uint32_t n = 0;
+  for (uint32_t y = 0; y < tiles_y; ++y) n += owned_in_row(tiles_x, y, tiles_x, rank, world);
+  return n;
+}
+
+}  // namespace gs
