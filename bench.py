@@ -1,0 +1,390 @@
+#!/usr/bin/env python
+"""bench.py — frames/sec of the splat hot path (sort + project + bin + raster) on B200.
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (CUDA, through the C ABI)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle restatement)
+
+A "step" is one full frame of the workload: the worker sort request plus the instanced draw
+(reference index.js:438-455 + 184-207), synchronously with the same camera.
+N = 1 workload = BASELINE.json configs[1]: train-like 1 M synthetic splats, 1920x1080, fixed camera.
+N > 1: the same scene, the FRAME sharded by 16x16 screen tile over the ranks (every rank holds the full
+splat table and the full draw order), one NCCL all-gather of finished RGBA8 tiles per frame -> strong scaling.
+
+`value` : frames/s with the scene resident in HBM and the frame left in HBM (device-timed, CUDA events on the
+          library's stream, L2 flushed between steps).
+`e2e`   : frames/s through gs_render with HOST buffers: camera matrices in, RGBA8 frame out to pinned host memory,
+          both copies inside the timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import importlib
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "frames/sec @1920x1080 (sort + splat raster, 1 M synthetic train-like splats)"
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def algorithmic_bytes(st: dict) -> dict:
+    """SURVEY.md 8(d) per-frame algorithmic bytes, from the counters the library returns."""
+    N, V, V2, D, T = st["n_splats"], st["n_sorted"], st["n_visible"], st["n_instances"], st["n_tiles"]
+    P = st["width"] * st["height"]
+    return {
+        "sort": 20 * N + 8 * V,               # K1: 16 B centre + 4 B sizeAlpha read, depth + index write
+        "project": 8 * V + 16 * V + 32 * V2,  # K2 (without the key emission, counted under bin)
+        "bin": 8 * D + 68 * D + 4 * D + 8 * T,  # key emission + K3 4 passes + K4
+        "raster": 36 * D + 4 * P,             # K5: sorted values + 32 B record per instance + RGBA8 frame
+        "total": 20 * N + 32 * V + 32 * V2 + 116 * D + 8 * T + 4 * P,
+    }
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,utilization.gpu,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, uuid: str):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", uuid, f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self) -> dict:
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [l.strip().split(", ") for l in open(self.f.name) if l.strip()]
+        os.unlink(self.f.name)
+        sm, smax, power, reasons = [], [], [], set()
+        for r in rows:
+            if len(r) < 9:
+                continue
+            try:
+                util = float(r[3])
+                if util >= 10.0:  # under load
+                    sm.append(float(r[0]))
+                smax.append(float(r[1]))
+                power.append(float(r[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.strip().lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "power_w_max": max(power) if power else None, "samples": len(rows), "samples_under_load": len(sm),
+                "reasons": sorted(reasons)}
+
+
+def build_scene(gs, args):
+    sc = gs.scenes
+    n, w, h, seed, cutout = sc.CONFIGS[args.workload]
+    if args.splats:
+        n = args.splats
+    rows = gs.synth_splats(n, seed)
+    fr = sc.make_frame(sc.fixed_camera(w, h), sc.demo_object(), w, h, sc.demo_cutout() if cutout else None)
+    return rows, fr, n, w, h
+
+
+# ------------------------------------------------------------------------------------------------------
+# reference arm: the reference's own CPU implementation of the path (oracle restatement; Node/WebGL absent)
+# ------------------------------------------------------------------------------------------------------
+def cpu_frame_time(orc, cs, cc, m, fr, w, h, budget_s: float, threads: int):
+    """One reference frame on the host: sortSplats on ONE thread (the reference has one Web Worker,
+    index.js:229) + software raster on all cores.  If a full frame exceeds the budget, a band of rows is shaded and
+    the raster time is scaled by rows/band (the sort is always run in full)."""
+    t0 = time.perf_counter()
+    order = orc.sort(m, fr.view, fr.cutout)
+    t_sort = time.perf_counter() - t0
+    # probe with 1/16 of the rows (centre band) to pick the sample size
+    band = max(16, h // 16)
+    y0 = (h - band) // 2
+    t0 = time.perf_counter()
+    orc.render(cs, cc, order, fr.proj, fr.modelview, w, h, fr.focal, nthreads=threads, rows=(y0, y0 + band))
+    t_probe = time.perf_counter() - t0
+    est_full = t_probe * h / band
+    if est_full <= budget_s:
+        rows = (0, h)
+    else:
+        nb = int(max(band, min(h, h * budget_s / est_full)))
+        rows = ((h - nb) // 2, (h - nb) // 2 + nb)
+    return order, t_sort, rows
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    gs = importlib.import_module("aframe-gaussian-splatting_b200")
+    from oracle import oracle as orc
+    orc.build()
+    rows, fr, n, w, h = build_scene(gs, args)
+    threads = os.cpu_count() or 1
+    cs, cc, m = orc.pack(rows)
+    total_budget = 150.0
+    per_step = total_budget / max(1, args.steps + args.warmup)
+    order, t_sort, band = cpu_frame_time(orc, cs, cc, m, fr, w, h, per_step, threads)
+    times = []
+    for i in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        order = orc.sort(m, fr.view, fr.cutout)
+        t1 = time.perf_counter()
+        orc.render(cs, cc, order, fr.proj, fr.modelview, w, h, fr.focal, nthreads=threads, rows=band)
+        t2 = time.perf_counter()
+        if i >= args.warmup:
+            times.append((t1 - t0) + (t2 - t1) * h / (band[1] - band[0]))
+    ms = 1000.0 * float(np.mean(times))
+    fps = 1000.0 / ms
+    sample = (f"sortSplats restatement on 1 thread + software raster on {threads} threads; "
+              + ("full frames" if band == (0, h) else f"rows {band[0]}..{band[1]} of {h} shaded per step, raster time scaled by {h}/{band[1]-band[0]}"))
+    line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64 sort keys + f32 shading", "data": "synthetic",
+            "config": {"workload": args.workload, "n_splats": n, "width": w, "height": h, "camera": "fixed"},
+            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    gs = importlib.import_module("aframe-gaussian-splatting_b200")
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU path")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    gs.build.build_library()
+    ctx = gs.SplatContext(local)
+    stream = torch.cuda.ExternalStream(ctx._lib.gs_stream(ctx._h), device=dev)
+
+    rows, fr, n, w, h = build_scene(gs, args)
+    ctx.push_splats(rows)  # scene resident in HBM before any timing
+    sharded = world > 1
+    if sharded:
+        ctx.set_shard(rank, world)
+    tiles_per_rank = max(ctx.owned_tiles(w, h, r, world) for r in range(world))
+
+    flags = gs.GS_RENDER_OUT_DEVICE | (gs.GS_RENDER_OUT_TILED if sharded else 0)
+    params = ctx.make_params(fr, fmt=gs.GS_FORMAT_RGBA8, flags=flags)
+    with torch.cuda.stream(stream):
+        frame_dev = torch.zeros(h * w * 4, dtype=torch.uint8, device=dev)
+        tiles_dev = torch.zeros(tiles_per_rank * 1024, dtype=torch.uint8, device=dev) if sharded else None
+        gathered = torch.zeros(world * tiles_per_rank * 1024, dtype=torch.uint8, device=dev) if sharded else None
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    stream.synchronize()
+
+    def step_device():
+        if not sharded:
+            return ctx.render_raw(params, frame_dev.data_ptr())
+        st = ctx.render_raw(params, tiles_dev.data_ptr())
+        with torch.cuda.stream(stream):
+            dist.all_gather_into_tensor(gathered, tiles_dev)
+        stream.synchronize()
+        ctx.assemble_tiles(gathered.data_ptr(), tiles_per_rank, world, w, h, gs.GS_FORMAT_RGBA8, frame_dev.data_ptr())
+        return st
+
+    def timed(fn, steps, collect=None):
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        for a, b in ev:
+            with torch.cuda.stream(stream):
+                flush.zero_()  # L2 flush between timed iterations (outside the event pair)
+                a.record(stream)
+            st = fn()
+            with torch.cuda.stream(stream):
+                b.record(stream)
+            if collect is not None and st is not None:
+                collect.append(st.as_dict())
+        stream.synchronize()
+        return [a.elapsed_time(b) for a, b in ev]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    uuid = str(torch.cuda.get_device_properties(dev).uuid)
+    sampler = ClockSampler(uuid if uuid.startswith("GPU-") else "GPU-" + uuid) if rank == 0 else None
+
+    # ---- value: device-resident frames ----
+    stats = []
+    barrier()
+    t_dev = timed(step_device, args.steps, stats)
+    barrier()
+    total_ms = float(sum(t_dev))
+    if world > 1:
+        t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    ms_per_step = total_ms / args.steps
+    fps = 1000.0 / ms_per_step
+
+    # ---- e2e: host buffers through the public C-ABI call, copies inside the timed region ----
+    e2e = None
+    if not sharded:
+        host_frame = ctx.pinned_array((h, w, 4), np.uint8)
+        p_host = ctx.make_params(fr, fmt=gs.GS_FORMAT_RGBA8, flags=0)
+
+        def step_host():
+            return ctx.render_raw(p_host, host_frame.ctypes.data)
+        for _ in range(3):
+            step_host()
+        barrier()
+        t_h = timed(step_host, args.steps)
+        barrier()
+        e2e_ms = float(sum(t_h)) / args.steps
+        e2e = {"value": 1000.0 / e2e_ms, "unit": "frames/s", "ms_per_step": e2e_ms,
+               "h2d_bytes_per_step": C.sizeof(gs.GsRenderParams), "d2h_bytes_per_step": h * w * 4,
+               "note": "camera/projection matrices are the only per-frame input (kernel arguments); RGBA8 frame read back to pinned host memory"}
+    else:
+        host_frame = ctx.pinned_array((h, w, 4), np.uint8)
+
+        def step_host():
+            st = step_device()
+            ctx.memcpy_d2h(host_frame, frame_dev.data_ptr(), h * w * 4)
+            return st
+        for _ in range(3):
+            step_host()
+        barrier()
+        t_h = timed(step_host, args.steps)
+        barrier()
+        tot = float(sum(t_h))
+        t = torch.tensor([tot], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item()) / args.steps
+        e2e = {"value": 1000.0 / e2e_ms, "unit": "frames/s", "ms_per_step": e2e_ms,
+               "h2d_bytes_per_step": C.sizeof(gs.GsRenderParams), "d2h_bytes_per_step": h * w * 4}
+
+    # keep the GPU loaded long enough for nvidia-smi to observe the clocks under this workload
+    if sampler is not None:
+        t_end = time.time() + 1.2
+        while time.time() < t_end:
+            step_device()
+    elif world > 1:
+        t_end = time.time() + 1.2
+        while time.time() < t_end:
+            step_device()
+    clocks = sampler.stop() if sampler is not None else None
+
+    if rank == 0:
+        st = {k: float(np.mean([s[k] for s in stats])) for k in stats[0]}
+        for k in ("n_splats", "n_sorted", "n_visible", "n_instances", "n_tiles", "width", "height", "kernel_launches", "n_dropped"):
+            st[k] = int(stats[0][k])
+        peak, peak_src = load_peaks()
+        ab = algorithmic_bytes(st)
+        stage_ms = {"sort": st["ms_sort"], "project": st["ms_project"], "bin": st["ms_bin"], "raster": st["ms_raster"]}
+        dom = max(stage_ms, key=stage_ms.get)
+        def roof(name):
+            ms = stage_ms[name]
+            ach = ab[name] / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
+            return {"bytes": ab[name], "ms": ms, "achieved_gbs": ach, "frac": ach / peak}
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tp):
+            try:
+                traffic = json.load(open(tp)).get(dom)
+            except Exception:
+                traffic = None
+        r = roof(dom)
+        line = {
+            "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64 sort keys + f32 shading", "data": "synthetic",
+            "config": {"workload": args.workload, "n_splats": n, "width": w, "height": h, "camera": "fixed",
+                       "parallelism": "1 GPU" if world == 1 else f"screen-tile sharding x{world} + NCCL all-gather of RGBA8 tiles",
+                       "l2": "flushed between timed steps (256 MiB memset outside the event pair)",
+                       "counters": {k: st[k] for k in ("n_splats", "n_sorted", "n_visible", "n_instances", "n_tiles")}},
+            "msplats_per_s": n * fps / 1e6,
+            "e2e": e2e,
+            "gpu_launches": int(st["kernel_launches"]) * args.steps + (args.steps if sharded else 0),
+            "clocks": clocks,
+            "roofline": {"kernel": {"sort": "k_depth_cull+k_key_hist+k_radix<D1,D2>", "project": "k_project", "bin": "k_emit+k_radix<T1,T2>+k_tile_scan",
+                                    "raster": "k_raster"}[dom],
+                         "bound": "hbm", "achieved": r["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": r["frac"],
+                         "traffic": traffic, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": ab[dom], "ms_per_launch": stage_ms[dom],
+                         "note": "k_raster is FP32-ALU bound (one exp + ~12 FMA per pixel-splat pair), reported against HBM as SURVEY.md 8d prescribes"},
+            "stages": {k: roof(k) for k in stage_ms},
+            "frame": {"bytes": ab["total"], "ms_device": st["ms_total"], "achieved_gbs": ab["total"] / (st["ms_total"] * 1e-3) / 1e9,
+                      "frac": ab["total"] / (st["ms_total"] * 1e-3) / 1e9 / peak},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            from oracle import oracle as orc
+            orc.build()
+            threads = os.cpu_count() or 1
+            cs, cc, m = orc.pack(rows)
+            order, t_sort, band = cpu_frame_time(orc, cs, cc, m, fr, w, h, 15.0, threads)
+            ts = []
+            for _ in range(3):
+                t0 = time.perf_counter(); orc.sort(m, fr.view, fr.cutout); ts.append(time.perf_counter() - t0)
+            t0 = time.perf_counter()
+            orc.render(cs, cc, order, fr.proj, fr.modelview, w, h, fr.focal, nthreads=threads, rows=band)
+            t_r = (time.perf_counter() - t0) * h / (band[1] - band[0])
+            t_frame = float(np.median(ts)) + t_r
+            line["cpu_baseline"] = {"value": 1.0 / t_frame, "unit": "frames/s", "cores": threads, "kind": "port",
+                                    "sort_ms_1thread": 1000 * float(np.median(ts)), "raster_ms": 1000 * t_r,
+                                    "sample": ("one frame: sortSplats restatement on 1 thread (median of 3) + software raster on %d threads, " % threads)
+                                    + ("full frame" if band == (0, h) else f"rows {band[0]}..{band[1]} of {h}, scaled")}
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="train_1m_1080p")
+    ap.add_argument("--splats", type=int, default=0, help="override the workload's splat count (debug)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

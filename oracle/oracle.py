@@ -48,6 +48,7 @@ def lib():
         L.orc_sort_compact.restype = C.c_int
         L.orc_project.restype = C.c_int
         L.orc_render.restype = C.c_int
+        L.orc_render_rows.restype = C.c_int
         L.orc_ply_to_splat.restype = C.c_int64
         L.orc_ply_to_splat.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p]
         L.orc_sizeof_proj.restype = C.c_int
@@ -112,7 +113,8 @@ def project(center_scale, cov_color, order, proj, mv, width, height, focal) -> n
     return out[:count]
 
 
-def render(center_scale, cov_color, order, proj, mv, width, height, focal, bg=(0, 0, 0, 0), nthreads=None, unorm8=False):
+def render(center_scale, cov_color, order, proj, mv, width, height, focal, bg=(0, 0, 0, 0), nthreads=None, unorm8=False,
+           rows=None):
     """Fragment shader + blend (index.js:170-181) -> ((H,W,4) f32 frame, row 0 = bottom; stats dict)."""
     cs = np.ascontiguousarray(center_scale, np.float32).reshape(-1, 4)
     cc = np.ascontiguousarray(cov_color, np.uint32).reshape(-1, 4)
@@ -122,9 +124,11 @@ def render(center_scale, cov_color, order, proj, mv, width, height, focal, bg=(0
     st = RenderStats()
     if nthreads is None:
         nthreads = os.cpu_count() or 1
-    rc = lib().orc_render(_p(cs), _p(cc), _p(o), C.c_uint32(o.shape[0]), _p(np.ascontiguousarray(proj, np.float32)),
-                          _p(np.ascontiguousarray(mv, np.float32)), C.c_uint32(width), C.c_uint32(height), C.c_float(focal),
-                          _p(bgv), _p(out), C.c_int(nthreads), C.c_int(1 if unorm8 else 0), C.byref(st))
+    r0, r1 = (0, height) if rows is None else rows  # rows=(y0, y1): shade only that band (bounded-sample timing)
+    rc = lib().orc_render_rows(_p(cs), _p(cc), _p(o), C.c_uint32(o.shape[0]), _p(np.ascontiguousarray(proj, np.float32)),
+                               _p(np.ascontiguousarray(mv, np.float32)), C.c_uint32(width), C.c_uint32(height), C.c_float(focal),
+                               _p(bgv), _p(out), C.c_int(nthreads), C.c_int(1 if unorm8 else 0), C.byref(st),
+                               C.c_uint32(r0), C.c_uint32(r1))
     assert rc == 0
     return out, {"n_order": st.n_order, "n_visible": st.n_visible, "fragments": st.fragments}
 
