@@ -1,0 +1,137 @@
+"""Multi-GPU frame sharding: one process per GPU, torch.distributed for the plumbing.
+
+The reference has no multi-GPU path (one worker + one GL context).  Here the FRAME is sharded, not the splat
+table: rank r rasters the 16x16 tiles with (tx + ty) % world == r.  Every rank keeps the full 36 B/splat table
+in its own HBM (80 M splats = 2.9 GB of 180 GB) and computes the same global draw order, so every pixel is
+composited on exactly one GPU in exactly the reference's order - the sharded frame is bit-identical to the
+single-GPU frame.  The only exchange step is one all-gather of finished RGBA tiles per frame
+(width*height*4 bytes in total, 8.3 MB at 1080p), followed by an un-tiling kernel.
+
+`TileSharding` is pure host arithmetic (also used by the gloo CPU tests); `ShardedRenderer` drives a
+SplatContext per rank.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Callable, Optional
+
+import numpy as np
+
+TILE = 16
+
+
+@dataclass(frozen=True)
+class TileSharding:
+    width: int
+    height: int
+    world: int
+
+    @property
+    def tiles_x(self) -> int:
+        return (self.width + TILE - 1) // TILE
+
+    @property
+    def tiles_y(self) -> int:
+        return (self.height + TILE - 1) // TILE
+
+    def owner(self, tx: int, ty: int) -> int:
+        return (tx + ty) % self.world
+
+    def owned_in_row(self, ty: int, upto_x: int, rank: int) -> int:
+        """tiles tx in [0, upto_x) of row ty owned by `rank` (mirrors csrc/gs_raster.cu owned_in_row)."""
+        r0 = (rank + self.world - (ty % self.world)) % self.world
+        return (upto_x - 1 - r0) // self.world + 1 if upto_x > r0 else 0
+
+    def slot(self, tx: int, ty: int, rank: int) -> int:
+        """index of tile (tx, ty) inside rank's packed tile buffer (mirrors owned_slot)."""
+        base = (ty // self.world) * self.tiles_x
+        for y in range((ty // self.world) * self.world, ty):
+            base += self.owned_in_row(y, self.tiles_x, rank)
+        return base + self.owned_in_row(ty, tx, rank)
+
+    def owned_tiles(self, rank: int) -> int:
+        return sum(self.owned_in_row(y, self.tiles_x, rank) for y in range(self.tiles_y))
+
+    @property
+    def tiles_per_rank(self) -> int:
+        """every rank pads its buffer to the largest share so the all-gather is uniform"""
+        return max(self.owned_tiles(r) for r in range(self.world))
+
+    def pack_owned(self, frame: np.ndarray, rank: int) -> np.ndarray:
+        """full (H, W, C) frame -> (tiles_per_rank, 256, C) buffer holding this rank's tiles (host reference)."""
+        c = frame.shape[2]
+        out = np.zeros((self.tiles_per_rank, TILE * TILE, c), frame.dtype)
+        for ty in range(self.tiles_y):
+            for tx in range(self.tiles_x):
+                if self.owner(tx, ty) != rank:
+                    continue
+                blk = np.zeros((TILE, TILE, c), frame.dtype)
+                src = frame[ty * TILE:(ty + 1) * TILE, tx * TILE:(tx + 1) * TILE]
+                blk[: src.shape[0], : src.shape[1]] = src
+                out[self.slot(tx, ty, rank)] = blk.reshape(TILE * TILE, c)
+        return out
+
+    def assemble(self, gathered: np.ndarray) -> np.ndarray:
+        """(world, tiles_per_rank, 256, C) gathered buffers -> (H, W, C) frame (host reference of k_assemble)."""
+        c = gathered.shape[-1]
+        frame = np.zeros((self.height, self.width, c), gathered.dtype)
+        for ty in range(self.tiles_y):
+            for tx in range(self.tiles_x):
+                r = self.owner(tx, ty)
+                blk = gathered[r, self.slot(tx, ty, r)].reshape(TILE, TILE, c)
+                dst = frame[ty * TILE:(ty + 1) * TILE, tx * TILE:(tx + 1) * TILE]
+                dst[...] = blk[: dst.shape[0], : dst.shape[1]]
+        return frame
+
+
+class ShardedRenderer:
+    """One rank of a frame-sharded render.
+
+    render_tiles(frame_inputs) must return this rank's packed tiles as a torch tensor of shape
+    (tiles_per_rank * 256 * C,) on the rank's device; `assemble(gathered, out)` un-tiles.  On GPUs both are the
+    C ABI (gs_render with GS_RENDER_OUT_TILED, gs_assemble_tiles); the gloo tests inject host versions.
+    """
+
+    def __init__(self, sharding: TileSharding, rank: int, render_tiles: Callable, assemble: Callable, process_group=None):
+        self.sharding, self.rank = sharding, rank
+        self._render_tiles, self._assemble, self.pg = render_tiles, assemble, process_group
+
+    def render(self, frame_inputs, out=None):
+        import torch.distributed as dist
+        import torch
+        mine = self._render_tiles(frame_inputs)
+        gathered = torch.empty((self.sharding.world * mine.numel(),), dtype=mine.dtype, device=mine.device)
+        if self.sharding.world > 1:
+            dist.all_gather_into_tensor(gathered, mine, group=self.pg)
+        else:
+            gathered.copy_(mine)
+        return self._assemble(gathered, out)
+
+
+def make_gpu_sharded_renderer(ctx, frame_like, rank: int, world: int, fmt: int = 0, process_group=None):
+    """Wire a SplatContext into a ShardedRenderer (RGBA8 by default).  Returns (renderer, frame tensor)."""
+    import torch
+    from ._lib import GS_RENDER_OUT_DEVICE, GS_RENDER_OUT_TILED
+    w, h = frame_like.width, frame_like.height
+    sh = TileSharding(w, h, world)
+    px = 4 if fmt == 0 else 16
+    dev = torch.device("cuda", ctx.device)
+    ctx.set_shard(rank, world)
+    stream = torch.cuda.ExternalStream(ctx._lib.gs_stream(ctx._h), device=dev)
+    with torch.cuda.stream(stream):
+        tiles = torch.zeros(sh.tiles_per_rank * 256 * px, dtype=torch.uint8, device=dev)
+        frame = torch.zeros(h * w * px, dtype=torch.uint8, device=dev)
+    stream.synchronize()
+
+    def render_tiles(fi):
+        p = ctx.make_params(fi, fmt=fmt, flags=GS_RENDER_OUT_DEVICE | GS_RENDER_OUT_TILED)
+        ctx.render_raw(p, tiles.data_ptr())
+        return tiles
+
+    def assemble(gathered, out):
+        torch.cuda.current_stream(dev).synchronize()
+        dst = frame if out is None else out
+        ctx.assemble_tiles(gathered.data_ptr(), sh.tiles_per_rank, world, w, h, fmt, dst.data_ptr())
+        return dst
+
+    return ShardedRenderer(sh, rank, render_tiles, assemble, process_group), frame
