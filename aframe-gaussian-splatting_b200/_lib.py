@@ -19,11 +19,11 @@ class GsStats(C.Structure):
         ("n_instances", C.c_uint64), ("n_tiles", C.c_uint32), ("width", C.c_uint32), ("height", C.c_uint32),
         ("min_depth", C.c_double), ("max_depth", C.c_double),
         ("ms_sort", C.c_float), ("ms_project", C.c_float), ("ms_bin", C.c_float), ("ms_raster", C.c_float),
-        ("ms_total", C.c_float), ("kernel_launches", C.c_uint32), ("reserved", C.c_uint32),
+        ("ms_total", C.c_float), ("kernel_launches", C.c_uint32), ("n_instances_kept", C.c_uint32),
     ]
 
     def as_dict(self):
-        return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
+        return {k: getattr(self, k) for k, _ in self._fields_ }
 
 
 class GsRenderParams(C.Structure):

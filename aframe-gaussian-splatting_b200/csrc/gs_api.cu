@@ -75,40 +75,10 @@ static int ensure_table(gs_context *c, uint64_t need) {
   return GS_OK;
 }
 
-static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
-
-// (re)build the status block: counters + every look-back status array, zeroed by ONE memset per frame
-static int ensure_status(gs_context *c) {
-  const size_t tiles_n = ((size_t)c->scratch_cap + kRadixTile - 1) / kRadixTile + 1;
-  const size_t tiles_e = ((size_t)c->scratch_cap + kEmitTile - 1) / kEmitTile + 1;
-  const size_t tiles_i = ((size_t)c->cap_inst + kRadixTile - 1) / kRadixTile + 1;
-  size_t off = 0;
-  const size_t o_ctr = off; off = align_up(off + sizeof(FrameCounters), 256);
-  const size_t o_d1 = off; off = align_up(off + tiles_n * 256 * 4, 256);
-  const size_t o_d2 = off; off = align_up(off + tiles_n * 256 * 4, 256);
-  const size_t o_e = off; off = align_up(off + tiles_e * 8, 256);
-  const size_t o_t1 = off; off = align_up(off + tiles_i * 256 * 4, 256);
-  const size_t o_t2 = off; off = align_up(off + tiles_i * 256 * 4, 256);
-  if (off != c->status_block_bytes || !c->status_block) {
-    if (c->status_block) cudaFree(c->status_block);
-    c->status_block = nullptr;
-    GS_CUDA(c, cudaMalloc(&c->status_block, off));
-    c->status_block_bytes = off;
-  }
-  char *b = (char *)c->status_block;
-  c->counters = (FrameCounters *)(b + o_ctr);
-  c->status_d1 = (uint32_t *)(b + o_d1);
-  c->status_d2 = (uint32_t *)(b + o_d2);
-  c->status_emit = (uint32_t *)(b + o_e);
-  c->status_t1 = (uint32_t *)(b + o_t1);
-  c->status_t2 = (uint32_t *)(b + o_t2);
-  return GS_OK;
-}
-
 static int ensure_scratch(gs_context *c) {
   if (c->scratch_cap >= c->cap && c->depth) return GS_OK;
   dev_free(c->depth); dev_free(c->idx_a); dev_free(c->dig_a); dev_free(c->order);
-  dev_free(c->proj_rec); dev_free(c->rect);
+  dev_free(c->proj_rec); dev_free(c->rect); dev_free(c->table_n); dev_free(c->tile_total);
   const size_t n = c->cap;
   GS_CUDA(c, dev_alloc(&c->depth, n));
   GS_CUDA(c, dev_alloc(&c->idx_a, n));
@@ -116,22 +86,28 @@ static int ensure_scratch(gs_context *c) {
   GS_CUDA(c, dev_alloc(&c->order, n));
   GS_CUDA(c, dev_alloc(&c->proj_rec, 2 * n));
   GS_CUDA(c, dev_alloc(&c->rect, n));
+  c->table_n_stride = (uint32_t)((n + kRadixTile - 1) / kRadixTile + 1);
+  GS_CUDA(c, dev_alloc(&c->table_n, (size_t)256 * c->table_n_stride));
+  GS_CUDA(c, dev_alloc(&c->tile_total, (n + kEmitTile - 1) / kEmitTile + 1));
   c->scratch_cap = c->cap;
   c->have_order = false;
-  return ensure_status(c);
+  return GS_OK;
 }
 
 static int ensure_instances(gs_context *c, uint64_t need) {
   if (need <= c->cap_inst && c->inst_rec) return GS_OK;
   if (need >= (1ull << 30)) return fail(c, GS_ERR_CAPACITY, "more than 2^30 tile instances in one frame");
   dev_free(c->inst_tile); dev_free(c->inst_idx); dev_free(c->inst_dig_b); dev_free(c->inst_idx_b); dev_free(c->inst_rec);
+  dev_free(c->table_d);
+  c->table_d_stride = (uint32_t)((need + kRadixTile - 1) / kRadixTile + 1);
+  GS_CUDA(c, dev_alloc(&c->table_d, (size_t)256 * c->table_d_stride));
   GS_CUDA(c, dev_alloc(&c->inst_tile, need));
   GS_CUDA(c, dev_alloc(&c->inst_idx, need));
   GS_CUDA(c, dev_alloc(&c->inst_dig_b, need));
   GS_CUDA(c, dev_alloc(&c->inst_idx_b, need));
   GS_CUDA(c, dev_alloc(&c->inst_rec, 2 * need));
   c->cap_inst = need;
-  return ensure_status(c);
+  return GS_OK;
 }
 
 static int ensure_tiles(gs_context *c, uint32_t n_tiles) {
@@ -205,6 +181,8 @@ extern "C" int gs_create(int device_ordinal, gs_context **out_ctx) {
       tab.push_back(strtod(buf, nullptr));
     }
   c->quirk_n = (int)tab.size();
+  if ((e = cudaMalloc((void **)&c->counters, sizeof(FrameCounters))) != cudaSuccess) return bail("cudaMalloc", e);
+  if ((e = cudaMalloc((void **)&c->totals, 512 * sizeof(uint32_t))) != cudaSuccess) return bail("cudaMalloc", e);
   if ((e = cudaMalloc((void **)&c->quirk_table, tab.size() * sizeof(double))) != cudaSuccess) return bail("cudaMalloc", e);
   if ((e = cudaMemcpy(c->quirk_table, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice)) != cudaSuccess)
     return bail("cudaMemcpy", e);
@@ -220,7 +198,7 @@ extern "C" int gs_destroy(gs_context *c) {
   dev_free(c->depth); dev_free(c->idx_a); dev_free(c->dig_a); dev_free(c->order); dev_free(c->proj_rec); dev_free(c->rect);
   dev_free(c->inst_tile); dev_free(c->inst_idx); dev_free(c->inst_dig_b); dev_free(c->inst_idx_b); dev_free(c->inst_rec);
   dev_free(c->tile_count); dev_free(c->tile_start); dev_free(c->quirk_table);
-  if (c->status_block) cudaFree(c->status_block);
+  dev_free(c->table_n); dev_free(c->table_d); dev_free(c->tile_total); dev_free(c->totals); dev_free(c->counters);
   if (c->frame_dev) cudaFree(c->frame_dev);
   if (c->counters_host) cudaFreeHost(c->counters_host);
   for (auto &ev : c->ev)
@@ -305,9 +283,8 @@ static void fill_sort_consts(SortConsts &sc, const float view[4], const float *c
 // enqueue the sort kernels (counters must have been zeroed)
 static uint32_t enqueue_sort(gs_context *c, const SortConsts &sc) {
   launch_depth_cull(c, sc);
-  launch_key_hist(c);
   launch_depth_radix(c);
-  return 4;
+  return 7;
 }
 
 static void stats_from_counters(gs_context *c) {
@@ -318,6 +295,7 @@ static void stats_from_counters(gs_context *c) {
   s.n_dropped = h.n_dropped;
   s.n_visible = h.n_visible;
   s.n_instances = h.n_inst;
+  s.n_instances_kept = h.n_inst_kept;
   s.min_depth = h.n_valid ? dec_f64(~h.min_enc) : INFINITY;
   s.max_depth = h.n_valid ? dec_f64(h.max_enc) : -INFINITY;
 }
@@ -331,7 +309,7 @@ extern "C" int gs_sort(gs_context *c, const float view[4], const float *cutout16
   if (rc) return rc;
   SortConsts sc;
   fill_sort_consts(sc, view, cutout16_or_null);
-  GS_CUDA(c, cudaMemsetAsync(c->status_block, 0, c->status_block_bytes, c->stream));
+  GS_CUDA(c, cudaMemsetAsync(c->counters, 0, sizeof(FrameCounters), c->stream));
   GS_CUDA(c, cudaEventRecord(c->ev[0], c->stream));
   const uint32_t launches = enqueue_sort(c, sc);
   GS_CUDA(c, cudaGetLastError());
@@ -428,7 +406,7 @@ extern "C" int gs_render(gs_context *c, const gs_render_params *p, void *out_rgb
 
   for (int attempt = 0; attempt < 8; ++attempt) {
     uint32_t launches = 0;
-    GS_CUDA(c, cudaMemsetAsync(c->status_block, 0, c->status_block_bytes, c->stream));
+    GS_CUDA(c, cudaMemsetAsync(c->counters, 0, sizeof(FrameCounters), c->stream));
     GS_CUDA(c, cudaMemsetAsync(c->tile_count, 0, sizeof(uint32_t) * ((size_t)rc.n_tiles + 1), c->stream));
     GS_CUDA(c, cudaEventRecord(c->ev[0], c->stream));
     if (reuse) {
@@ -444,7 +422,7 @@ extern "C" int gs_render(gs_context *c, const gs_render_params *p, void *out_rgb
     launch_emit(c, rc);
     launch_tile_radix(c);
     launch_tile_scan(c, rc);
-    launches += 4;
+    launches += 9;
     GS_CUDA(c, cudaEventRecord(c->ev[3], c->stream));
     launch_raster(c, rc, out_dev);
     launches += 1;

@@ -40,19 +40,15 @@ constexpr unsigned long long kFlagMask64 = 3ull << 62;
 
 // Device-resident per-frame counters: zeroed by one memset at the start of every sort/render.
 struct FrameCounters {
-  unsigned long long min_enc;  // order-preserving encoding of the fp64 min depth (atomicMin)
-  unsigned long long max_enc;  // ... max depth (atomicMax)
-  unsigned long long n_inst;   // D: emitted tile instances (incl. instances of non-owned tiles)
+  unsigned long long min_enc;  // bit-inverted order-preserving encoding of the fp64 min depth (atomicMax)
+  unsigned long long max_enc;  // order-preserving encoding of the fp64 max depth (atomicMax)
+  unsigned long long n_inst;   // D: emitted tile instances (bounding-rectangle candidates)
   uint32_t n_valid;            // V: splats passing the worker filter
   uint32_t n_inrange;          // V - dropped: entries with a key in [0,65535]
   uint32_t n_dropped;          // quirk Q5
   uint32_t n_visible;          // V2
-  uint32_t n_inst_kept;        // instances surviving the tile-ownership filter
+  uint32_t n_inst_kept;        // instances surviving the exact footprint test and the tile-ownership filter
   uint32_t overflow;           // instance buffer too small: frame must be re-run
-  uint32_t ticket[6];          // dynamic tile tickets of the look-back kernels
-  uint32_t pad[3];
-  uint32_t hist_lo[256], hist_hi[256];    // depth-key digit histograms
-  uint32_t thist_lo[256], thist_hi[256];  // tile-id digit histograms
 };
 
 struct RenderConsts {
@@ -95,10 +91,10 @@ struct gs_context {
   uint32_t *order = nullptr;     // draw order (== reference sortedIndexes)
   float4 *proj_rec = nullptr;    // 2 x float4 per splat
   uint32_t *rect = nullptr;      // packed tile rect per splat
-  uint32_t *status_d1 = nullptr, *status_d2 = nullptr;  // look-back status [tiles][256]
-  uint32_t *status_emit = nullptr;                      // [emit tiles]
-  void *status_block = nullptr;  // one allocation holding counters + all status arrays
-  size_t status_block_bytes = 0;
+  uint32_t *table_n = nullptr;   // radix chunk histograms of the depth passes [256][table_n_stride]
+  uint32_t table_n_stride = 0;
+  uint32_t *totals = nullptr;    // [512]: digit totals of the depth / tile passes
+  uint32_t *tile_total = nullptr;  // instances per 1024-entry emission slice
 
   // ---- per-instance scratch (sized to cap_inst) ----
   uint64_t cap_inst = 0;
@@ -107,7 +103,8 @@ struct gs_context {
   uint8_t *inst_dig_b = nullptr;
   uint32_t *inst_idx_b = nullptr;
   float4 *inst_rec = nullptr;    // 2 x float4 per instance, sorted by (tile, draw order)
-  uint32_t *status_t1 = nullptr, *status_t2 = nullptr;
+  uint32_t *table_d = nullptr;   // radix chunk histograms of the tile passes [256][table_d_stride]
+  uint32_t table_d_stride = 0;
 
   // ---- per-frame tables ----
   uint32_t tiles_cap = 0;
@@ -136,7 +133,6 @@ namespace gs {
 // -- launchers (each .cu file owns its kernels) --
 // sort
 void launch_depth_cull(gs_context *c, const SortConsts &sc);
-void launch_key_hist(gs_context *c);
 void launch_depth_radix(gs_context *c);  // two passes -> c->order
 // pack
 void launch_pack(gs_context *c, const uint8_t *rows_dev, uint32_t first, uint32_t n);

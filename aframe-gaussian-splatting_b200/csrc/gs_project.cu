@@ -3,9 +3,9 @@
 //
 //   k_project  : fp32 restatement of the vertex shader, op for op (no FMA contraction), producing a
 //                32 B projected record per splat + its packed tile rectangle.
-//   k_emit     : walks the draw order (== reference sortedIndexes), scans the per-splat tile counts with
-//                a decoupled look-back and writes (tile, splat) instances in draw order, so that a STABLE
-//                sort by tile id alone reproduces the reference's back-to-front order inside every tile.
+//   k_count    : instances per 1024-entry slice of the draw order (== reference sortedIndexes) + frame total D.
+//   k_emit     : prefix of those totals + in-slice scan -> writes (tile, splat) instances in draw order, so that a
+//                STABLE sort by tile id alone reproduces the reference's back-to-front order inside every tile.
 //   k_tile_scan: exclusive scan of the per-tile instance counts -> tile ranges for the raster.
 #include "gs_common.cuh"
 
@@ -148,36 +148,80 @@ __device__ __forceinline__ uint32_t rect_count(uint32_t r) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// K3: ordered instance emission.  Tile of 1024 draw-order entries per CTA iteration.
+// K3a: instances per emission tile (1024 consecutive draw-order entries) and the frame total D.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kEmitThreads) k_emit(const uint32_t *__restrict__ order,
-                                                       const uint32_t *__restrict__ rect, RenderConsts rc,
-                                                       uint64_t cap_inst, uint16_t *__restrict__ inst_tile,
-                                                       uint32_t *__restrict__ inst_idx, uint32_t *__restrict__ tile_count,
-                                                       unsigned long long *status, FrameCounters *ctr) {
-  __shared__ uint32_t s_off[kEmitTile + 1];
-  __shared__ uint32_t s_rect[kEmitTile];
-  __shared__ uint32_t s_idx[kEmitTile];
-  __shared__ uint32_t h_lo[256], h_hi[256];
-  __shared__ uint32_t s_warp[kEmitThreads / 32];
-  __shared__ uint32_t s_tile, s_vis, s_kept;
-  __shared__ unsigned long long s_base;
+__global__ void __launch_bounds__(kEmitThreads) k_count(const uint32_t *__restrict__ order,
+                                                        const uint32_t *__restrict__ rect,
+                                                        uint32_t *__restrict__ tile_total, FrameCounters *ctr) {
+  __shared__ uint32_t s_sum[kEmitThreads / 32], s_vis[kEmitThreads / 32];
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t nv = ctr->n_valid;
   const uint32_t num_tiles = (nv + kEmitTile - 1) / kEmitTile;
-  h_lo[tid] = 0;
-  h_hi[tid] = 0;
-  if (tid == 0) { s_vis = 0; s_kept = 0; }
-  __syncthreads();
-
-  while (true) {
-    if (tid == 0) s_tile = atomicAdd(&ctr->ticket[4], 1u);
-    __syncthreads();
-    const uint32_t tile = s_tile;
-    if (tile >= num_tiles) break;
-    // each thread owns 4 consecutive draw-order entries
+  for (uint32_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
     const uint32_t j0 = tile * kEmitTile + tid * kEmitItems;
-    uint32_t cnt[kEmitItems], sum = 0, vis = 0;
+    uint32_t sum = 0, vis = 0;
+#pragma unroll
+    for (int k = 0; k < kEmitItems; ++k) {
+      const uint32_t j = j0 + k;
+      if (j < nv) {
+        const uint32_t r = __ldg(rect + __ldg(order + j));
+        sum += rect_count(r);
+        vis += (r != kNoRect);
+      }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      vis += __shfl_xor_sync(0xffffffffu, vis, o);
+    }
+    if (lane == 0) { s_sum[warp] = sum; s_vis[warp] = vis; }
+    __syncthreads();
+    if (tid == 0) {
+      uint32_t t = 0, v = 0;
+      for (int k = 0; k < kEmitThreads / 32; ++k) { t += s_sum[k]; v += s_vis[k]; }
+      tile_total[tile] = t;
+      if (t) atomicAdd(&ctr->n_inst, (unsigned long long)t);
+      if (v) atomicAdd(&ctr->n_visible, v);
+    }
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K3b: ordered instance emission.  Instance (entry j, k-th tile of its rectangle) lands at
+// position prefix(j) + k, so the instance array is in draw order whatever the execution order.
+// One thread per instance (balanced expansion); every candidate tile of the bounding rectangle is
+// tested exactly against the r<=2 footprint (closest point of the tile's pixel-centre box in the splat's
+// (px,py) frame) and rejected tiles are written as kNoTile, which the T1 pass drops.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kEmitThreads, 6) k_emit(const uint32_t *__restrict__ order,
+                                                       const uint32_t *__restrict__ rect,
+                                                       const float4 *__restrict__ proj_rec, RenderConsts rc,
+                                                       uint64_t cap_inst, const uint32_t *__restrict__ tile_total,
+                                                       uint16_t *__restrict__ inst_tile, uint32_t *__restrict__ inst_idx,
+                                                       uint32_t *__restrict__ tile_count, FrameCounters *ctr) {
+  __shared__ uint32_t s_off[kEmitTile];
+  __shared__ uint32_t s_rect[kEmitTile];
+  __shared__ uint32_t s_idx[kEmitTile];
+  __shared__ uint32_t s_warp[kEmitThreads / 32];
+  __shared__ unsigned long long s_red[kEmitThreads / 32];
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t nv = ctr->n_valid;
+  const uint32_t num_tiles = (nv + kEmitTile - 1) / kEmitTile;
+  if (ctr->n_inst > cap_inst) {  // instance buffer too small: the host regrows it and re-runs the frame
+    if (blockIdx.x == 0 && tid == 0) ctr->overflow = 1u;
+    return;
+  }
+  unsigned long long base = 0;
+  uint32_t summed_upto = 0;  // tile_total[0, summed_upto) is already in `base`
+  for (uint32_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    // ---- exclusive prefix of the tile totals (block reduction over the not-yet-summed range) ----
+    unsigned long long part = 0;
+    for (uint32_t t = summed_upto + tid; t < tile; t += kEmitThreads) part += tile_total[t];
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    if (lane == 0) s_red[warp] = part;
+    // ---- load the tile's entries ----
+    const uint32_t j0 = tile * kEmitTile + tid * kEmitItems;
+    uint32_t cnt[kEmitItems], sum = 0;
 #pragma unroll
     for (int k = 0; k < kEmitItems; ++k) {
       const uint32_t j = j0 + k;
@@ -189,93 +233,83 @@ __global__ void __launch_bounds__(kEmitThreads) k_emit(const uint32_t *__restric
       s_idx[tid * kEmitItems + k] = idx;
       s_rect[tid * kEmitItems + k] = r;
       cnt[k] = rect_count(r);
-      vis += (r != kNoRect);
       sum += cnt[k];
     }
-    // block exclusive scan of `sum`
     uint32_t incl = sum;
     for (int o = 1; o < 32; o <<= 1) {
       const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
       if (lane >= (uint32_t)o) incl += t;
     }
     if (lane == 31) s_warp[warp] = incl;
-    for (int o = 16; o > 0; o >>= 1) vis += __shfl_xor_sync(0xffffffffu, vis, o);
-    if (lane == 0 && vis) atomicAdd(&s_vis, vis);
     __syncthreads();
-    uint32_t wbase = 0, total = 0;
-    for (uint32_t k = 0; k < kEmitThreads / 32; ++k) {
-      if (k < warp) wbase += s_warp[k];
-      total += s_warp[k];
-    }
+    uint32_t wbase = 0;
+    for (uint32_t k = 0; k < warp; ++k) wbase += s_warp[k];
+    for (int k = 0; k < kEmitThreads / 32; ++k) base += s_red[k];
+    summed_upto = tile;
     uint32_t run = wbase + incl - sum;
 #pragma unroll
     for (int k = 0; k < kEmitItems; ++k) {
       s_off[tid * kEmitItems + k] = run;
       run += cnt[k];
     }
-    if (tid == 0) {
-      s_off[kEmitTile] = total;
-      // decoupled look-back on one running total; 64-bit status word = 2 flag bits | 62-bit value
-      unsigned long long *st = status + tile;
-      unsigned long long excl = 0;
-      if (tile == 0) {
-        st_relaxed64(st, kFlagIncl64 | (unsigned long long)total);
-      } else {
-        st_relaxed64(st, kFlagAgg64 | (unsigned long long)total);
-        uint32_t p = tile - 1;
-        while (true) {
-          const unsigned long long v = ld_relaxed64(status + p);
-          if ((v & kFlagMask64) == 0) continue;
-          excl += v & ~kFlagMask64;
-          if (v & kFlagIncl64) break;
-          --p;
-        }
-        st_relaxed64(st, kFlagIncl64 | (excl + total));
+    __syncthreads();
+    // ---- expansion: one thread per instance, strided over the slice's instance space (balanced whatever
+    //      the rectangle sizes); the entry of instance e is found by binary search in the scanned offsets ----
+    const uint32_t total = s_off[kEmitTile - 1] + rect_count(s_rect[kEmitTile - 1]);
+    for (uint32_t e = tid; e < total; e += kEmitThreads) {
+      uint32_t lo = 0, hi = kEmitTile;
+#pragma unroll
+      for (int it = 0; it < 10; ++it) {  // kEmitTile == 1024
+        const uint32_t mid = (lo + hi) >> 1;
+        if (s_off[mid] <= e) lo = mid; else hi = mid;
       }
-      const unsigned long long inc = excl + total;
-      s_base = excl;
-      if (tile == num_tiles - 1) ctr->n_inst = inc;
-      if (inc > cap_inst) ctr->overflow = 1u;
+      const uint32_t r = s_rect[lo];
+      const uint32_t idx = s_idx[lo];
+      const uint32_t k = e - s_off[lo];
+      const uint32_t tx0 = r & 255u, w = ((r >> 8) & 255u) - tx0 + 1u, ty0 = (r >> 16) & 255u;
+      const uint32_t n_t = w * ((r >> 24) - ty0 + 1u);
+      // k / w for k < 65536, w <= 256: float quotient of (k + 0.5) is never within rounding of an integer
+      const uint32_t dy_t = (uint32_t)__fdividef((float)k + 0.5f, (float)w);
+      const uint32_t tx = tx0 + (k - dy_t * w), ty = ty0 + dy_t;
+      bool keep = (rc.shard_world <= 1) || (((tx + ty) % rc.shard_world) == rc.shard_rank);
+      if (keep && n_t > 1) {
+        // footprint geometry: neighbouring instances share the splat, so these gathers mostly hit L1
+        const float4 r0 = __ldg(proj_rec + 2 * (size_t)idx);                       // cx, cy, a1x, a1y
+        const float2 r1 = __ldg((const float2 *)(proj_rec + 2 * (size_t)idx + 1));  // a2x, a2y
+        // pixel-centre box of the tile, relative to the splat centre
+        const float xa = (float)(tx * kTile) + 0.5f - r0.x, xb = xa + 15.0f;
+        const float ya = (float)(ty * kTile) + 0.5f - r0.y, yb = ya + 15.0f;
+        const bool in_x = (xa <= 0.0f) && (xb >= 0.0f), in_y = (ya <= 0.0f) && (yb >= 0.0f);
+        if (!(in_x && in_y)) {
+          float qmin = 3.0e38f;
+          if (!in_x) {  // nearest vertical edge, minimise over y on it
+            const float dx = (xa > 0.0f) ? xa : xb;
+            const float px0 = dx * r1.x, py0 = dx * r0.z;
+            float t = -__fdividef(px0 * r1.y + py0 * r0.w, r1.y * r1.y + r0.w * r0.w);
+            t = fminf(fmaxf(t, ya), yb);
+            const float px = px0 + t * r1.y, py = py0 + t * r0.w;
+            qmin = px * px + py * py;
+          }
+          if (!in_y) {  // nearest horizontal edge, minimise over x on it
+            const float dy = (ya > 0.0f) ? ya : yb;
+            const float px0 = dy * r1.y, py0 = dy * r0.w;
+            float t = -__fdividef(px0 * r1.x + py0 * r0.z, r1.x * r1.x + r0.z * r0.z);
+            t = fminf(fmaxf(t, xa), xb);
+            const float px = px0 + t * r1.x, py = py0 + t * r0.z;
+            qmin = fminf(qmin, px * px + py * py);
+          }
+          keep = !(qmin > 4.02f);  // r^2 <= 4 with slack for fp32 rounding of the closest-point search
+        }
+      }
+      uint32_t t = kNoTile;
+      if (keep) {
+        t = ty * rc.tiles_x + tx;
+        atomicAdd(tile_count + t, 1u);
+      }
+      inst_tile[base + e] = (uint16_t)t;
+      inst_idx[base + e] = idx;
     }
     __syncthreads();
-    const unsigned long long base = s_base;
-    if (base + total <= cap_inst) {
-      uint32_t kept = 0;
-      for (uint32_t e = tid; e < total; e += kEmitThreads) {
-        // find the entry j with s_off[j] <= e < s_off[j+1]
-        uint32_t lo = 0, hi = kEmitTile;
-        while (hi - lo > 1) {
-          const uint32_t mid = (lo + hi) >> 1;
-          if (s_off[mid] <= e) lo = mid; else hi = mid;
-        }
-        const uint32_t r = s_rect[lo];
-        const uint32_t k = e - s_off[lo];
-        const uint32_t tx0 = r & 255u, w = ((r >> 8) & 255u) - tx0 + 1u, ty0 = (r >> 16) & 255u;
-        const uint32_t ty = ty0 + k / w, tx = tx0 + k % w;
-        uint32_t t = ty * rc.tiles_x + tx;
-        const bool owned = (rc.shard_world <= 1) || (((tx + ty) % rc.shard_world) == rc.shard_rank);
-        if (owned) {
-          ++kept;
-          atomicAdd(&h_lo[t & 255u], 1u);
-          atomicAdd(&h_hi[t >> 8], 1u);
-          atomicAdd(tile_count + t, 1u);
-        } else {
-          t = kNoTile;
-        }
-        inst_tile[base + e] = (uint16_t)t;
-        inst_idx[base + e] = s_idx[lo];
-      }
-      for (int o = 16; o > 0; o >>= 1) kept += __shfl_xor_sync(0xffffffffu, kept, o);
-      if (lane == 0 && kept) atomicAdd(&s_kept, kept);
-    }
-    __syncthreads();
-  }
-  __syncthreads();
-  if (h_lo[tid]) atomicAdd(&ctr->thist_lo[tid], h_lo[tid]);
-  if (h_hi[tid]) atomicAdd(&ctr->thist_hi[tid], h_hi[tid]);
-  if (tid == 0) {
-    if (s_vis) atomicAdd(&ctr->n_visible, s_vis);
-    if (s_kept) atomicAdd(&ctr->n_inst_kept, s_kept);
   }
 }
 
@@ -318,11 +352,12 @@ void launch_project(gs_context *c, const RenderConsts &rc) {
 
 void launch_emit(gs_context *c, const RenderConsts &rc) {
   uint64_t tiles = ((uint64_t)c->n + kEmitTile - 1) / kEmitTile;
-  const uint64_t cap = (uint64_t)c->sm_count * 4;
+  const uint64_t cap = (uint64_t)c->sm_count * 8;
   if (tiles > cap) tiles = cap;
   if (tiles < 1) tiles = 1;
-  k_emit<<<(int)tiles, kEmitThreads, 0, c->stream>>>(c->order, c->rect, rc, c->cap_inst, c->inst_tile, c->inst_idx,
-                                                     c->tile_count, (unsigned long long *)c->status_emit, c->counters);
+  k_count<<<(int)tiles, kEmitThreads, 0, c->stream>>>(c->order, c->rect, c->tile_total, c->counters);
+  k_emit<<<(int)tiles, kEmitThreads, 0, c->stream>>>(c->order, c->rect, c->proj_rec, rc, c->cap_inst, c->tile_total,
+                                                     c->inst_tile, c->inst_idx, c->tile_count, c->counters);
 }
 
 void launch_tile_scan(gs_context *c, const RenderConsts &rc) {

@@ -111,56 +111,21 @@ __global__ void __launch_bounds__(256) k_depth_cull(const float4 *__restrict__ c
 }
 
 // ---------------------------------------------------------------------------------------------
-// K1b: key + digit histograms (index.js:560-563).  Reads 4 B per splat.
-// ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_key_hist(const float *__restrict__ depth, uint32_t n, FrameCounters *ctr) {
-  __shared__ uint32_t h_lo[256], h_hi[256];
-  __shared__ uint32_t s_in, s_drop;
-  h_lo[threadIdx.x] = 0;
-  h_hi[threadIdx.x] = 0;
-  if (threadIdx.x == 0) { s_in = 0; s_drop = 0; }
-  __syncthreads();
-  if (ctr->n_valid != 0) {
-    const DepthRange dr = load_depth_range(ctr);
-    uint32_t in = 0, drop = 0;
-    const uint32_t stride = gridDim.x * blockDim.x;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-      const float d = __ldg(depth + i);
-      if (d == GS_DEPTH_REJECT) continue;
-      const int32_t key = depth_key(d, dr.min_depth, dr.depth_inv);
-      if (key < 0 || key > 65535) { ++drop; continue; }  // typed-array write out of range: dropped (Q5)
-      ++in;
-      atomicAdd(&h_lo[key & 255], 1u);
-      atomicAdd(&h_hi[key >> 8], 1u);
-    }
-    for (int o = 16; o > 0; o >>= 1) {
-      in += __shfl_xor_sync(0xffffffffu, in, o);
-      drop += __shfl_xor_sync(0xffffffffu, drop, o);
-    }
-    if ((threadIdx.x & 31) == 0) {
-      if (in) atomicAdd(&s_in, in);
-      if (drop) atomicAdd(&s_drop, drop);
-    }
-  }
-  __syncthreads();
-  if (h_lo[threadIdx.x]) atomicAdd(&ctr->hist_lo[threadIdx.x], h_lo[threadIdx.x]);
-  if (h_hi[threadIdx.x]) atomicAdd(&ctr->hist_hi[threadIdx.x], h_hi[threadIdx.x]);
-  if (threadIdx.x == 0) {
-    if (s_in) atomicAdd(&ctr->n_inrange, s_in);
-    if (s_drop) atomicAdd(&ctr->n_dropped, s_drop);
-  }
-}
-
-// ---------------------------------------------------------------------------------------------
-// Stable 8-bit radix pass with decoupled look-back (single read, single write per element).
+// Stable 8-bit radix pass = three fully parallel kernels (no inter-CTA spinning):
+//   k_radix_hist<PASS>   : per-chunk (4096 elements) digit histogram        -> table[digit][chunk]
+//   k_radix_scan<PASS>   : per-digit exclusive scan over the chunks (in place) + digit totals
+//   k_radix_scatter<PASS>: per chunk: stable in-chunk ranks (warp match_any) + table offset -> scatter
+// PASS_D1/D2: 16-bit depth key (index.js:557-567) low/high byte.  PASS_T1/T2: 16-bit tile id low/high byte;
+// T2's scatter gathers the 32 B projected record of each instance into its final per-tile slot.
 // ---------------------------------------------------------------------------------------------
 enum { PASS_D1 = 0, PASS_D2 = 1, PASS_T1 = 2, PASS_T2 = 3 };
 
 struct RadixArgs {
   FrameCounters *ctr;
-  uint32_t *status;
-  uint32_t n_host;  // D1: number of resident splats
-  uint64_t cap_inst;
+  uint32_t *table;   // [256][stride]
+  uint32_t *totals;  // [256]
+  uint32_t stride;
+  uint32_t n_host;   // D1: number of resident splats
   // depth passes
   const float *depth;
   uint32_t *idx_a;
@@ -176,91 +141,191 @@ struct RadixArgs {
 };
 
 template <int PASS>
-__global__ void __launch_bounds__(kRadixThreads) k_radix(RadixArgs a) {
-  __shared__ uint32_t wcnt[kRadixThreads / 32][256];
-  __shared__ uint32_t tile_off[256];
-  __shared__ uint32_t s_warp_tot[8];
-  __shared__ uint32_t s_tile;
+__device__ __forceinline__ uint32_t pass_n(const RadixArgs &a) {
+  const FrameCounters *ctr = a.ctr;
+  if (PASS == PASS_D1) return ctr->n_valid ? a.n_host : 0u;
+  if (PASS == PASS_D2) return ctr->n_inrange;
+  if (PASS == PASS_T1) return ctr->overflow ? 0u : (uint32_t)ctr->n_inst;
+  return ctr->overflow ? 0u : ctr->n_inst_kept;
+}
+
+// digit (or kInvalidDigit), payload and next-pass digit of element i
+template <int PASS>
+__device__ __forceinline__ void load_elem(const RadixArgs &a, uint32_t i, const DepthRange &dr, uint32_t &digit,
+                                          uint32_t &pay, uint32_t &hi, uint32_t &dropped) {
+  digit = kInvalidDigit;
+  pay = 0;
+  hi = 0;
+  if (PASS == PASS_D1) {
+    const float d = __ldg(a.depth + i);
+    if (d != GS_DEPTH_REJECT) {
+      const int32_t key = depth_key(d, dr.min_depth, dr.depth_inv);
+      if (key >= 0 && key <= 65535) { digit = key & 255; hi = (uint32_t)key >> 8; pay = i; }
+      else ++dropped;  // typed-array write out of range: dropped (quirk Q5)
+    }
+  } else if (PASS == PASS_D2) {
+    digit = a.dig_a[i];
+    pay = a.idx_a[i];
+  } else if (PASS == PASS_T1) {
+    const uint16_t t = a.inst_tile[i];
+    if (t != kNoTile) { digit = t & 255; hi = (uint32_t)t >> 8; pay = a.inst_idx[i]; }
+  } else {
+    digit = a.inst_dig_b[i];
+    pay = a.inst_idx_b[i];
+  }
+}
+
+template <int PASS>
+__global__ void __launch_bounds__(kRadixThreads) k_radix_hist(RadixArgs a) {
+  __shared__ uint32_t h[256];
+  __shared__ uint32_t s_in, s_drop;
   FrameCounters *ctr = a.ctr;
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-
-  uint32_t n;
-  const uint32_t *hist;
-  if (PASS == PASS_D1) { n = a.n_host; hist = ctr->hist_lo; }
-  else if (PASS == PASS_D2) { n = ctr->n_inrange; hist = ctr->hist_hi; }
-  else if (PASS == PASS_T1) {
-    const unsigned long long d = ctr->n_inst;
-    n = ctr->overflow ? 0u : (uint32_t)d;
-    hist = ctr->thist_lo;
-  } else { n = ctr->overflow ? 0u : ctr->n_inst_kept; hist = ctr->thist_hi; }
-  const uint32_t num_tiles = (n + kRadixTile - 1) / kRadixTile;
-
-  // exclusive scan of the global digit histogram -> first output slot of each digit
-  uint32_t dbase;
-  {
-    const uint32_t h = hist[tid];
-    uint32_t incl = h;
-    for (int o = 1; o < 32; o <<= 1) {
-      const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= (uint32_t)o) incl += t;
-    }
-    if (lane == 31) s_warp_tot[warp] = incl;
-    __syncthreads();
-    uint32_t wbase = 0;
-    for (uint32_t k = 0; k < warp; ++k) wbase += s_warp_tot[k];
-    dbase = wbase + incl - h;
-  }
-
+  const uint32_t n = pass_n<PASS>(a);
+  const uint32_t num_chunks = (n + kRadixTile - 1) / kRadixTile;
   DepthRange dr{0.0, 0.0};
-  if (PASS == PASS_D1) {
-    if (ctr->n_valid == 0) return;
-    dr = load_depth_range(ctr);
-  }
+  if (PASS == PASS_D1 && n) dr = load_depth_range(ctr);
   if (PASS == PASS_D2) {
     // quirk Q5: the reference's output keeps length validCount; slots never written stay 0
     const uint32_t nv = ctr->n_valid;
     for (uint32_t j = n + blockIdx.x * blockDim.x + tid; j < nv; j += gridDim.x * blockDim.x) a.order[j] = 0u;
   }
-
-  while (true) {
-    if (tid == 0) s_tile = atomicAdd(&ctr->ticket[PASS], 1u);
-    for (uint32_t k = tid; k < (kRadixThreads / 32) * 256; k += kRadixThreads) (&wcnt[0][0])[k] = 0u;
+  if (tid == 0) { s_in = 0; s_drop = 0; }
+  uint32_t in = 0, drop = 0;
+  for (uint32_t c = blockIdx.x; c < num_chunks; c += gridDim.x) {
+    h[tid] = 0;
     __syncthreads();
-    const uint32_t tile = s_tile;
-    if (tile >= num_tiles) break;
-
-    // ---- load (warp-striped: consecutive lanes read consecutive elements) ----
-    const uint32_t base = tile * kRadixTile + warp * (32 * kRadixItems) + lane;
-    uint32_t digit[kRadixItems], pay[kRadixItems], rank[kRadixItems];
-    uint8_t hi[kRadixItems];
+    const uint32_t base = c * kRadixTile + warp * (32 * kRadixItems) + lane;
 #pragma unroll
     for (int s = 0; s < kRadixItems; ++s) {
+      const uint32_t i = base + s * 32;
+      if (i < n) {
+        uint32_t digit, pay, hi;
+        load_elem<PASS>(a, i, dr, digit, pay, hi, drop);
+        if (digit != kInvalidDigit) { atomicAdd(&h[digit], 1u); ++in; }
+      }
+    }
+    __syncthreads();
+    a.table[(size_t)tid * a.stride + c] = h[tid];
+    __syncthreads();
+  }
+  if (PASS == PASS_D1) {
+    for (int o = 16; o > 0; o >>= 1) {
+      in += __shfl_xor_sync(0xffffffffu, in, o);
+      drop += __shfl_xor_sync(0xffffffffu, drop, o);
+    }
+    __syncthreads();
+    if (lane == 0) { if (in) atomicAdd(&s_in, in); if (drop) atomicAdd(&s_drop, drop); }
+    __syncthreads();
+    if (tid == 0) {
+      if (s_in) atomicAdd(&ctr->n_inrange, s_in);
+      if (s_drop) atomicAdd(&ctr->n_dropped, s_drop);
+    }
+  }
+}
+
+// grid = 256 CTAs (one per digit)
+template <int PASS>
+__global__ void __launch_bounds__(256) k_radix_scan(RadixArgs a) {
+  __shared__ uint32_t s_warp[8];
+  __shared__ uint32_t s_carry;
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t n = pass_n<PASS>(a);
+  const uint32_t num_chunks = (n + kRadixTile - 1) / kRadixTile;
+  uint32_t *row = a.table + (size_t)blockIdx.x * a.stride;
+  if (tid == 0) s_carry = 0;
+  __syncthreads();
+  for (uint32_t b = 0; b < num_chunks; b += 256) {
+    const uint32_t i = b + tid;
+    const uint32_t v = (i < num_chunks) ? row[i] : 0u;
+    uint32_t incl = v;
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= (uint32_t)o) incl += t;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    uint32_t wbase = 0;
+    for (uint32_t k = 0; k < warp; ++k) wbase += s_warp[k];
+    const uint32_t carry = s_carry;
+    if (i < num_chunks) row[i] = carry + wbase + incl - v;
+    __syncthreads();
+    if (tid == 255) s_carry = carry + wbase + incl;
+    __syncthreads();
+  }
+  if (tid == 0) {
+    a.totals[blockIdx.x] = s_carry;
+    if (PASS == PASS_T1 && s_carry) atomicAdd(&a.ctr->n_inst_kept, s_carry);
+  }
+}
+
+// 512 threads x 8 elements per chunk: 16 warps rank their 256-element slices independently (an 8-step
+// dependent chain each), then one scan over the 16 warp counters per digit orders the slices.
+constexpr int kScatThreads = 512;
+constexpr int kScatItems = kRadixTile / kScatThreads;  // 8
+constexpr int kScatWarps = kScatThreads / 32;          // 16
+
+template <int PASS>
+__global__ void __launch_bounds__(kScatThreads, 2) k_radix_scatter(RadixArgs a) {
+  __shared__ uint32_t wcnt[kScatWarps][256];
+  __shared__ uint32_t tile_off[256];  // global slot of the digit's first element MINUS its slot in the staged chunk
+  __shared__ uint32_t s_loc[256];     // slot of the digit's first element in the staged (locally sorted) chunk
+  __shared__ uint32_t s_warp_tot[8];
+  __shared__ uint32_t s_pay[kRadixTile];
+  __shared__ uint8_t s_hi[kRadixTile];
+  __shared__ uint8_t s_dig[kRadixTile];
+  __shared__ uint32_t s_total;
+  FrameCounters *ctr = a.ctr;
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t n = pass_n<PASS>(a);
+  const uint32_t num_chunks = (n + kRadixTile - 1) / kRadixTile;
+  if (blockIdx.x >= num_chunks) return;
+
+  // block-wide exclusive scan over the 256 digit slots (threads >= 256 contribute 0)
+  auto scan256 = [&](uint32_t v) -> uint32_t {
+    uint32_t incl = v;
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= (uint32_t)o) incl += t;
+    }
+    __syncthreads();  // previous users of s_warp_tot are done
+    if (lane == 31 && warp < 8) s_warp_tot[warp] = incl;
+    __syncthreads();
+    uint32_t wbase = 0;
+    for (uint32_t k = 0; k < warp && k < 8; ++k) wbase += s_warp_tot[k];
+    return wbase + incl - v;
+  };
+
+  // first output slot of each digit
+  const uint32_t dbase = scan256(tid < 256 ? a.totals[tid] : 0u);
+  DepthRange dr{0.0, 0.0};
+  if (PASS == PASS_D1) dr = load_depth_range(ctr);
+
+  for (uint32_t c = blockIdx.x; c < num_chunks; c += gridDim.x) {
+    // this chunk's per-digit offset: issued first so its latency hides behind the ranking
+    const uint32_t toff = tid < 256 ? __ldg(a.table + (size_t)tid * a.stride + c) : 0u;
+    for (uint32_t k = tid; k < kScatWarps * 256; k += kScatThreads) (&wcnt[0][0])[k] = 0u;
+    // ---- load (warp-striped: consecutive lanes read consecutive elements) ----
+    const uint32_t base = c * kRadixTile + warp * (32 * kScatItems) + lane;
+    uint32_t digit[kScatItems], pay[kScatItems], rank[kScatItems];
+    uint8_t hi[kScatItems];
+    uint32_t dummy = 0;
+#pragma unroll
+    for (int s = 0; s < kScatItems; ++s) {
       const uint32_t i = base + s * 32;
       digit[s] = kInvalidDigit;
       pay[s] = 0;
       hi[s] = 0;
       if (i < n) {
-        if (PASS == PASS_D1) {
-          const float d = __ldg(a.depth + i);
-          if (d != GS_DEPTH_REJECT) {
-            const int32_t key = depth_key(d, dr.min_depth, dr.depth_inv);
-            if (key >= 0 && key <= 65535) { digit[s] = key & 255; hi[s] = (uint8_t)(key >> 8); pay[s] = i; }
-          }
-        } else if (PASS == PASS_D2) {
-          digit[s] = a.dig_a[i];
-          pay[s] = a.idx_a[i];
-        } else if (PASS == PASS_T1) {
-          const uint16_t t = a.inst_tile[i];
-          if (t != kNoTile) { digit[s] = t & 255; hi[s] = (uint8_t)(t >> 8); pay[s] = a.inst_idx[i]; }
-        } else {
-          digit[s] = a.inst_dig_b[i];
-          pay[s] = a.inst_idx_b[i];
-        }
+        uint32_t h8;
+        load_elem<PASS>(a, i, dr, digit[s], pay[s], h8, dummy);
+        hi[s] = (uint8_t)h8;
       }
     }
+    __syncthreads();
     // ---- stable rank inside the warp (input order = lane order within a step, steps in order) ----
 #pragma unroll
-    for (int s = 0; s < kRadixItems; ++s) {
+    for (int s = 0; s < kScatItems; ++s) {
       const uint32_t d = digit[s];
       const uint32_t peers = __match_any_sync(0xffffffffu, d);
       const uint32_t lt = __popc(peers & ((1u << lane) - 1u));
@@ -272,51 +337,50 @@ __global__ void __launch_bounds__(kRadixThreads) k_radix(RadixArgs a) {
       rank[s] = prior + lt;
     }
     __syncthreads();
-    // ---- thread `tid` owns digit `tid`: scan over warps, publish, look back ----
-    {
-      uint32_t total = 0;
+    // ---- thread `tid` < 256 owns digit `tid`: exclusive scan over the warps, then over the digits ----
+    uint32_t total = 0;
+    if (tid < 256) {
 #pragma unroll
-      for (int w = 0; w < kRadixThreads / 32; ++w) {
-        const uint32_t c = wcnt[w][tid];
+      for (int w = 0; w < kScatWarps; ++w) {
+        const uint32_t cnt = wcnt[w][tid];
         wcnt[w][tid] = total;
-        total += c;
+        total += cnt;
       }
-      uint32_t *st = a.status + (size_t)tile * 256 + tid;
-      uint32_t excl = 0;
-      if (tile == 0) {
-        st_relaxed(st, kFlagIncl | total);
-      } else {
-        st_relaxed(st, kFlagAgg | total);
-        uint32_t p = tile - 1;
-        while (true) {
-          const uint32_t v = ld_relaxed(a.status + (size_t)p * 256 + tid);
-          if ((v & kFlagMask) == 0) continue;
-          excl += v & kValMask;
-          if (v & kFlagIncl) break;
-          --p;
-        }
-        st_relaxed(st, kFlagIncl | (excl + total));
-      }
-      tile_off[tid] = dbase + excl;
+    }
+    const uint32_t loc = scan256(total);
+    if (tid < 256) {
+      s_loc[tid] = loc;
+      tile_off[tid] = dbase + toff - loc;
+      if (tid == 255) s_total = loc + total;
     }
     __syncthreads();
-    // ---- scatter ----
+    // ---- stage the chunk in shared memory in sorted order ----
 #pragma unroll
-    for (int s = 0; s < kRadixItems; ++s) {
+    for (int s = 0; s < kScatItems; ++s) {
       const uint32_t d = digit[s];
       if (d == kInvalidDigit) continue;
-      const uint32_t pos = tile_off[d] + wcnt[warp][d] + rank[s];
+      const uint32_t lp = s_loc[d] + wcnt[warp][d] + rank[s];
+      s_pay[lp] = pay[s];
+      s_dig[lp] = (uint8_t)d;
+      if (PASS == PASS_D1 || PASS == PASS_T1) s_hi[lp] = hi[s];
+    }
+    __syncthreads();
+    // ---- write out: consecutive threads write consecutive slots of the same digit run (coalesced) ----
+    const uint32_t nvalid = s_total;
+    for (uint32_t i = tid; i < nvalid; i += kScatThreads) {
+      const uint32_t pos = tile_off[s_dig[i]] + i;
+      const uint32_t p = s_pay[i];
       if (PASS == PASS_D1) {
-        a.idx_a[pos] = pay[s];
-        a.dig_a[pos] = hi[s];
+        a.idx_a[pos] = p;
+        a.dig_a[pos] = s_hi[i];
       } else if (PASS == PASS_D2) {
-        a.order[pos] = pay[s];
+        a.order[pos] = p;
       } else if (PASS == PASS_T1) {
-        a.inst_idx_b[pos] = pay[s];
-        a.inst_dig_b[pos] = hi[s];
+        a.inst_idx_b[pos] = p;
+        a.inst_dig_b[pos] = s_hi[i];
       } else {
-        const float4 r0 = __ldg(a.proj_rec + 2 * (size_t)pay[s]);
-        const float4 r1 = __ldg(a.proj_rec + 2 * (size_t)pay[s] + 1);
+        const float4 r0 = __ldg(a.proj_rec + 2 * (size_t)p);
+        const float4 r1 = __ldg(a.proj_rec + 2 * (size_t)p + 1);
         a.inst_rec[2 * (size_t)pos] = r0;
         a.inst_rec[2 * (size_t)pos + 1] = r1;
       }
@@ -337,16 +401,10 @@ void launch_depth_cull(gs_context *c, const SortConsts &sc) {
   k_depth_cull<<<grid, 256, 0, c->stream>>>(c->center_scale, c->size_alpha, c->n, sc, c->depth, c->counters);
 }
 
-void launch_key_hist(gs_context *c) {
-  const int grid = persistent_grid(c, c->n, 256 * 8, 8);
-  k_key_hist<<<grid, 256, 0, c->stream>>>(c->depth, c->n, c->counters);
-}
-
 static RadixArgs make_args(gs_context *c) {
   RadixArgs a{};
   a.ctr = c->counters;
   a.n_host = c->n;
-  a.cap_inst = c->cap_inst;
   a.depth = c->depth;
   a.idx_a = c->idx_a;
   a.dig_a = c->dig_a;
@@ -360,22 +418,32 @@ static RadixArgs make_args(gs_context *c) {
   return a;
 }
 
-void launch_depth_radix(gs_context *c) {
-  RadixArgs a = make_args(c);
-  const int grid = persistent_grid(c, c->n, kRadixTile, 4);
-  a.status = c->status_d1;
-  k_radix<PASS_D1><<<grid, kRadixThreads, 0, c->stream>>>(a);
-  a.status = c->status_d2;
-  k_radix<PASS_D2><<<grid, kRadixThreads, 0, c->stream>>>(a);
+template <int PASS>
+static void run_pass(gs_context *c, RadixArgs &a, uint64_t n_max) {
+  const int grid = persistent_grid(c, n_max, kRadixTile, 8);
+  k_radix_hist<PASS><<<grid, kRadixThreads, 0, c->stream>>>(a);
+  k_radix_scan<PASS><<<256, 256, 0, c->stream>>>(a);
+  k_radix_scatter<PASS><<<grid, kScatThreads, 0, c->stream>>>(a);
 }
 
+// index.js:557-567 as two stable 8-bit passes -> c->order (6 launches)
+void launch_depth_radix(gs_context *c) {
+  RadixArgs a = make_args(c);
+  a.table = c->table_n;
+  a.totals = c->totals;
+  a.stride = c->table_n_stride;
+  run_pass<PASS_D1>(c, a, c->n);
+  run_pass<PASS_D2>(c, a, c->n);
+}
+
+// stable sort of the tile instances by tile id (6 launches); T2 writes the per-tile record lists
 void launch_tile_radix(gs_context *c) {
   RadixArgs a = make_args(c);
-  const int grid = persistent_grid(c, c->cap_inst, kRadixTile, 4);
-  a.status = c->status_t1;
-  k_radix<PASS_T1><<<grid, kRadixThreads, 0, c->stream>>>(a);
-  a.status = c->status_t2;
-  k_radix<PASS_T2><<<grid, kRadixThreads, 0, c->stream>>>(a);
+  a.table = c->table_d;
+  a.totals = c->totals + 256;
+  a.stride = c->table_d_stride;
+  run_pass<PASS_T1>(c, a, c->cap_inst);
+  run_pass<PASS_T2>(c, a, c->cap_inst);
 }
 
 }  // namespace gs

@@ -48,7 +48,9 @@ def load_peaks():
 
 def algorithmic_bytes(st: dict) -> dict:
     """SURVEY.md 8(d) per-frame algorithmic bytes, from the counters the library returns."""
-    N, V, V2, D, T = st["n_splats"], st["n_sorted"], st["n_visible"], st["n_instances"], st["n_tiles"]
+    # D = tile instances whose tile really meets the footprint (the rejected bounding-box candidates that the emit
+    # and T1 kernels also touch are NOT counted: the claim stays conservative)
+    N, V, V2, D, T = st["n_splats"], st["n_sorted"], st["n_visible"], st["n_instances_kept"], st["n_tiles"]
     P = st["width"] * st["height"]
     return {
         "sort": 20 * N + 8 * V,               # K1: 16 B centre + 4 B sizeAlpha read, depth + index write
@@ -307,7 +309,7 @@ def run_ours(args):
 
     if rank == 0:
         st = {k: float(np.mean([s[k] for s in stats])) for k in stats[0]}
-        for k in ("n_splats", "n_sorted", "n_visible", "n_instances", "n_tiles", "width", "height", "kernel_launches", "n_dropped"):
+        for k in ("n_splats", "n_sorted", "n_visible", "n_instances", "n_instances_kept", "n_tiles", "width", "height", "kernel_launches", "n_dropped"):
             st[k] = int(stats[0][k])
         peak, peak_src = load_peaks()
         ab = algorithmic_bytes(st)
@@ -332,12 +334,12 @@ def run_ours(args):
             "config": {"workload": args.workload, "n_splats": n, "width": w, "height": h, "camera": "fixed",
                        "parallelism": "1 GPU" if world == 1 else f"screen-tile sharding x{world} + NCCL all-gather of RGBA8 tiles",
                        "l2": "flushed between timed steps (256 MiB memset outside the event pair)",
-                       "counters": {k: st[k] for k in ("n_splats", "n_sorted", "n_visible", "n_instances", "n_tiles")}},
+                       "counters": {k: st[k] for k in ("n_splats", "n_sorted", "n_visible", "n_instances", "n_instances_kept", "n_tiles")}},
             "msplats_per_s": n * fps / 1e6,
             "e2e": e2e,
             "gpu_launches": int(st["kernel_launches"]) * args.steps + (args.steps if sharded else 0),
             "clocks": clocks,
-            "roofline": {"kernel": {"sort": "k_depth_cull+k_key_hist+k_radix<D1,D2>", "project": "k_project", "bin": "k_emit+k_radix<T1,T2>+k_tile_scan",
+            "roofline": {"kernel": {"sort": "k_depth_cull+k_radix_{hist,scan,scatter}<D1,D2>", "project": "k_project", "bin": "k_count+k_emit+k_radix_{hist,scan,scatter}<T1,T2>+k_tile_scan",
                                     "raster": "k_raster"}[dom],
                          "bound": "hbm", "achieved": r["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": r["frac"],
                          "traffic": traffic, "peak_source": peak_src,

@@ -66,7 +66,7 @@ typedef struct gs_stats {
   uint32_t n_sorted;       /* V   splats passing the worker filter (index.js:548)            */
   uint32_t n_dropped;      /*     sorted entries whose 16-bit key fell outside [0,65535] (Q5)*/
   uint32_t n_visible;      /* V2  entries also passing the shader clip-cull (index.js:110-115)*/
-  uint64_t n_instances;    /* D   16x16 tile instances                                       */
+  uint64_t n_instances;    /*     16x16 tile candidates (bounding rectangles of the footprints)*/
   uint32_t n_tiles;        /* T   tiles in the frame                                         */
   uint32_t width, height;  /*     frame size (P = width*height)                              */
   double min_depth, max_depth; /* fp64 depth range of the sorted set (index.js:552-553)      */
@@ -76,7 +76,7 @@ typedef struct gs_stats {
   float ms_raster;         /* tile raster + composite                                        */
   float ms_total;          /* whole frame on the device (events on the context's stream)     */
   uint32_t kernel_launches;/* kernels launched by the call                                   */
-  uint32_t reserved;
+  uint32_t n_instances_kept;/* D  tile instances whose tile really meets the r<=2 footprint    */
 } gs_stats;
 
 /* ---- lifetime ---------------------------------------------------------------------------- */
