@@ -17,6 +17,8 @@ uint32_t owned_tiles_host(uint32_t width, uint32_t height, uint32_t rank, uint32
 }
 using namespace gs;
 
+static int drain(gs_context *c);
+
 static thread_local std::string g_create_error;
 
 #define GS_CUDA(ctx, expr)                                                                             \
@@ -119,13 +121,19 @@ static int ensure_tiles(gs_context *c, uint32_t n_tiles) {
   return GS_OK;
 }
 
-static int ensure_frame(gs_context *c, size_t bytes) {
-  if (bytes <= c->frame_bytes && c->frame_dev) return GS_OK;
-  if (c->frame_dev) cudaFree(c->frame_dev);
-  c->frame_dev = nullptr;
-  GS_CUDA(c, cudaMalloc(&c->frame_dev, bytes));
-  c->frame_bytes = bytes;
+static int ensure_frame(gs_context *c, gs_context::Slot &sl, size_t bytes) {
+  if (bytes <= sl.frame_bytes && sl.frame_dev) return GS_OK;
+  if (sl.frame_dev) cudaFree(sl.frame_dev);
+  sl.frame_dev = nullptr;
+  GS_CUDA(c, cudaMalloc(&sl.frame_dev, bytes));
+  sl.frame_bytes = bytes;
   return GS_OK;
+}
+
+static void drop_graphs(gs_context *c) {
+  for (auto &sl : c->slot)
+    for (auto &g : sl.graph)
+      if (g) { cudaGraphExecDestroy(g); g = nullptr; }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -168,10 +176,21 @@ extern "C" int gs_create(int device_ordinal, gs_context **out_ctx) {
   };
   if ((e = cudaSetDevice(device_ordinal)) != cudaSuccess) return bail("cudaSetDevice", e);
   if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+  if ((e = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
   for (auto &ev : c->ev)
     if ((e = cudaEventCreate(&ev)) != cudaSuccess) return bail("cudaEventCreate", e);
-  if ((e = cudaHostAlloc((void **)&c->counters_host, sizeof(FrameCounters), cudaHostAllocDefault)) != cudaSuccess)
-    return bail("cudaHostAlloc", e);
+  for (auto &sl : c->slot) {
+    for (auto &ev : sl.ev)
+      if ((e = cudaEventCreate(&ev)) != cudaSuccess) return bail("cudaEventCreate", e);
+    if ((e = cudaEventCreateWithFlags(&sl.ev_done, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
+    if ((e = cudaEventCreateWithFlags(&sl.ev_copied, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
+    if ((e = cudaMalloc((void **)&sl.ctr, sizeof(FrameCounters))) != cudaSuccess) return bail("cudaMalloc", e);
+    if ((e = cudaMalloc((void **)&sl.fp, sizeof(FrameParams))) != cudaSuccess) return bail("cudaMalloc", e);
+    if ((e = cudaHostAlloc((void **)&sl.ctr_host, sizeof(FrameCounters), cudaHostAllocDefault)) != cudaSuccess) return bail("cudaHostAlloc", e);
+    if ((e = cudaHostAlloc((void **)&sl.fp_host, sizeof(FrameParams), cudaHostAllocDefault)) != cudaSuccess) return bail("cudaHostAlloc", e);
+  }
+  if ((e = cudaMalloc((void **)&c->sort_hdr, sizeof(SortHeader))) != cudaSuccess) return bail("cudaMalloc", e);
+  c->use_graphs = getenv("GS_NO_GRAPH") == nullptr;
   // parseInt quirk table (gs_pack.cu): strtod("<d>e-<k>") for k = 323..7, d = 1..9, ascending
   std::vector<double> tab;
   for (int k = 323; k >= 7; --k)
@@ -181,7 +200,6 @@ extern "C" int gs_create(int device_ordinal, gs_context **out_ctx) {
       tab.push_back(strtod(buf, nullptr));
     }
   c->quirk_n = (int)tab.size();
-  if ((e = cudaMalloc((void **)&c->counters, sizeof(FrameCounters))) != cudaSuccess) return bail("cudaMalloc", e);
   if ((e = cudaMalloc((void **)&c->totals, 512 * sizeof(uint32_t))) != cudaSuccess) return bail("cudaMalloc", e);
   if ((e = cudaMalloc((void **)&c->quirk_table, tab.size() * sizeof(double))) != cudaSuccess) return bail("cudaMalloc", e);
   if ((e = cudaMemcpy(c->quirk_table, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice)) != cudaSuccess)
@@ -198,11 +216,21 @@ extern "C" int gs_destroy(gs_context *c) {
   dev_free(c->depth); dev_free(c->idx_a); dev_free(c->dig_a); dev_free(c->order); dev_free(c->proj_rec); dev_free(c->rect);
   dev_free(c->inst_tile); dev_free(c->inst_idx); dev_free(c->inst_dig_b); dev_free(c->inst_idx_b); dev_free(c->inst_rec);
   dev_free(c->tile_count); dev_free(c->tile_start); dev_free(c->quirk_table);
-  dev_free(c->table_n); dev_free(c->table_d); dev_free(c->tile_total); dev_free(c->totals); dev_free(c->counters);
-  if (c->frame_dev) cudaFree(c->frame_dev);
-  if (c->counters_host) cudaFreeHost(c->counters_host);
+  if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
+  drop_graphs(c);
+  dev_free(c->table_n); dev_free(c->table_d); dev_free(c->tile_total); dev_free(c->totals); dev_free(c->sort_hdr);
+  for (auto &sl : c->slot) {
+    dev_free(sl.ctr); dev_free(sl.fp);
+    if (sl.frame_dev) cudaFree(sl.frame_dev);
+    if (sl.ctr_host) cudaFreeHost(sl.ctr_host);
+    if (sl.fp_host) cudaFreeHost(sl.fp_host);
+    for (auto &ev : sl.ev) if (ev) cudaEventDestroy(ev);
+    if (sl.ev_done) cudaEventDestroy(sl.ev_done);
+    if (sl.ev_copied) cudaEventDestroy(sl.ev_copied);
+  }
   for (auto &ev : c->ev)
     if (ev) cudaEventDestroy(ev);
+  if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
   return GS_OK;
@@ -213,6 +241,8 @@ extern "C" int gs_destroy(gs_context *c) {
 // ---------------------------------------------------------------------------------------------
 extern "C" int gs_clear(gs_context *c) {
   if (!c) return GS_ERR_INVALID;
+  int rc0 = drain(c);
+  if (rc0) return rc0;
   c->n = 0;
   c->have_order = false;
   c->order_count = 0;
@@ -229,8 +259,9 @@ extern "C" int gs_push_splats(gs_context *c, const void *rows32, uint32_t n) {
   if (!c || (!rows32 && n)) return GS_ERR_INVALID;
   if (!n) return GS_OK;
   GS_CUDA(c, cudaSetDevice(c->device));
-  int rc = ensure_table(c, (uint64_t)c->n + n);
+  int rc = drain(c);
   if (rc) return rc;
+  if ((rc = ensure_table(c, (uint64_t)c->n + n))) return rc;
   uint8_t *rows_dev = nullptr;
   GS_CUDA(c, cudaMalloc((void **)&rows_dev, (size_t)n * 32));
   cudaError_t e = cudaMemcpyAsync(rows_dev, rows32, (size_t)n * 32, cudaMemcpyHostToDevice, c->stream);
@@ -251,8 +282,9 @@ extern "C" int gs_push_packed(gs_context *c, const float *center_scale4, const u
   if (!c || ((!center_scale4 || !cov_color4 || !size_alpha) && n)) return GS_ERR_INVALID;
   if (!n) return GS_OK;
   GS_CUDA(c, cudaSetDevice(c->device));
-  int rc = ensure_table(c, (uint64_t)c->n + n);
+  int rc = drain(c);
   if (rc) return rc;
+  if ((rc = ensure_table(c, (uint64_t)c->n + n))) return rc;
   GS_CUDA(c, cudaMemcpyAsync(c->center_scale + c->n, center_scale4, sizeof(float4) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
   GS_CUDA(c, cudaMemcpyAsync(c->cov_color + c->n, cov_color4, sizeof(uint4) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
   GS_CUDA(c, cudaMemcpyAsync(c->size_alpha + c->n, size_alpha, sizeof(float) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
@@ -280,15 +312,19 @@ static void fill_sort_consts(SortConsts &sc, const float view[4], const float *c
     for (int i = 0; i < 16; ++i) sc.cutout[i] = (double)cutout[i];
 }
 
-// enqueue the sort kernels (counters must have been zeroed)
-static uint32_t enqueue_sort(gs_context *c, const SortConsts &sc) {
-  launch_depth_cull(c, sc);
-  launch_depth_radix(c);
-  return 7;
+static int wait_slot(gs_context *c, gs_context::Slot &sl, gs_stats *stats);
+
+// finish whatever is in flight (before buffers are reallocated or the splat table changes)
+static int drain(gs_context *c) {
+  for (auto &sl : c->slot)
+    if (sl.pending) {
+      int rc = wait_slot(c, sl, nullptr);
+      if (rc) return rc;
+    }
+  return GS_OK;
 }
 
-static void stats_from_counters(gs_context *c) {
-  const FrameCounters &h = *c->counters_host;
+static void stats_from_counters(gs_context *c, const FrameCounters &h) {
   gs_stats &s = c->stats;
   s.n_splats = c->n;
   s.n_sorted = h.n_valid;
@@ -305,26 +341,31 @@ extern "C" int gs_sort(gs_context *c, const float view[4], const float *cutout16
   if (!c || !view) return GS_ERR_INVALID;
   if (c->n == 0) return fail(c, GS_ERR_EMPTY, "gs_sort before any push");
   GS_CUDA(c, cudaSetDevice(c->device));
-  int rc = ensure_scratch(c);
+  int rc = drain(c);
   if (rc) return rc;
-  SortConsts sc;
-  fill_sort_consts(sc, view, cutout16_or_null);
-  GS_CUDA(c, cudaMemsetAsync(c->counters, 0, sizeof(FrameCounters), c->stream));
+  if ((rc = ensure_scratch(c))) return rc;
+  gs_context::Slot &sl = c->slot[0];
+  memset(sl.fp_host, 0, sizeof(FrameParams));
+  fill_sort_consts(sl.fp_host->sc, view, cutout16_or_null);
+  GS_CUDA(c, cudaMemcpyAsync(sl.fp, sl.fp_host, sizeof(FrameParams), cudaMemcpyHostToDevice, c->stream));
+  GS_CUDA(c, cudaMemsetAsync(sl.ctr, 0, sizeof(FrameCounters), c->stream));
   GS_CUDA(c, cudaEventRecord(c->ev[0], c->stream));
-  const uint32_t launches = enqueue_sort(c, sc);
+  launch_depth_cull(c, sl.fp, sl.ctr);
+  launch_depth_radix(c, sl.ctr);
   GS_CUDA(c, cudaGetLastError());
   GS_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
-  GS_CUDA(c, cudaMemcpyAsync(c->counters_host, c->counters, sizeof(FrameCounters), cudaMemcpyDeviceToHost, c->stream));
+  GS_CUDA(c, cudaMemcpyAsync(c->sort_hdr, sl.ctr, sizeof(SortHeader), cudaMemcpyDeviceToDevice, c->stream));
+  GS_CUDA(c, cudaMemcpyAsync(sl.ctr_host, sl.ctr, sizeof(FrameCounters), cudaMemcpyDeviceToHost, c->stream));
   GS_CUDA(c, cudaStreamSynchronize(c->stream));
   memset(&c->stats, 0, sizeof(c->stats));
-  stats_from_counters(c);
-  c->stats.kernel_launches = launches;
+  stats_from_counters(c, *sl.ctr_host);
+  c->stats.kernel_launches = 7;
   float ms = 0;
   cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]);
   c->stats.ms_sort = ms;
   c->stats.ms_total = ms;
   c->have_order = true;
-  c->order_count = c->counters_host->n_valid;
+  c->order_count = sl.ctr_host->n_valid;
   if (out_count) *out_count = c->order_count;
   if (out_idx && c->order_count)
     GS_CUDA(c, cudaMemcpy(out_idx, c->order, sizeof(uint32_t) * (size_t)c->order_count, cudaMemcpyDeviceToHost));
@@ -346,16 +387,91 @@ extern "C" uint32_t gs_owned_tiles(uint32_t width, uint32_t height, uint32_t ran
   return owned_tiles_host(width, height, rank, world);
 }
 
-extern "C" int gs_render(gs_context *c, const gs_render_params *p, void *out_rgba, gs_stats *stats) {
-  if (!c || !p || !out_rgba) return GS_ERR_INVALID;
-  if (c->n == 0) return fail(c, GS_ERR_EMPTY, "gs_render before any push");
-  if (p->width == 0 || p->height == 0 || p->width > 4096 || p->height > 4096)
-    return fail(c, GS_ERR_INVALID, "frame size must be within 1..4096 per side");
-  if (p->out_format != GS_FORMAT_RGBA8 && p->out_format != GS_FORMAT_RGBA32F) return fail(c, GS_ERR_INVALID, "bad out_format");
-  GS_CUDA(c, cudaSetDevice(c->device));
+// Everything one frame does on the main stream; all per-frame inputs come from sl.fp (device memory), so the same
+// sequence can be captured once into a CUDA graph and replayed.
+static cudaError_t enqueue_frame(gs_context *c, gs_context::Slot &sl, bool reuse, uint32_t n_tiles, bool external_events) {
+  auto rec = [&](cudaEvent_t ev) {
+    return external_events ? cudaEventRecordWithFlags(ev, c->stream, cudaEventRecordExternal) : cudaEventRecord(ev, c->stream);
+  };
+  cudaError_t e;
+  if ((e = cudaMemcpyAsync(sl.fp, sl.fp_host, sizeof(FrameParams), cudaMemcpyHostToDevice, c->stream))) return e;
+  if ((e = cudaMemsetAsync(sl.ctr, 0, sizeof(FrameCounters), c->stream))) return e;
+  if ((e = cudaMemsetAsync(c->tile_count, 0, sizeof(uint32_t) * ((size_t)n_tiles + 1), c->stream))) return e;
+  if ((e = rec(sl.ev[0]))) return e;
+  uint32_t launches = 0;
+  if (reuse) {
+    if ((e = cudaMemcpyAsync(sl.ctr, c->sort_hdr, sizeof(SortHeader), cudaMemcpyDeviceToDevice, c->stream))) return e;
+  } else {
+    launch_depth_cull(c, sl.fp, sl.ctr);
+    launch_depth_radix(c, sl.ctr);
+    launches += 7;
+    if ((e = cudaMemcpyAsync(c->sort_hdr, sl.ctr, sizeof(SortHeader), cudaMemcpyDeviceToDevice, c->stream))) return e;
+  }
+  if ((e = rec(sl.ev[1]))) return e;
+  launch_project(c, sl.fp);
+  if ((e = rec(sl.ev[2]))) return e;
+  launch_emit(c, sl.fp, sl.ctr);
+  launch_tile_radix(c, sl.ctr);
+  launch_tile_scan(c, n_tiles);
+  if ((e = rec(sl.ev[3]))) return e;
+  launch_raster(c, sl.fp, n_tiles);
+  launches += 11;
+  if ((e = rec(sl.ev[4]))) return e;
+  sl.launches = launches;
+  return cudaGetLastError();
+}
 
-  RenderConsts rc;
-  memset(&rc, 0, sizeof(rc));
+static int launch_frame(gs_context *c, gs_context::Slot &sl, bool reuse, uint32_t n_tiles) {
+  // (re)capture when anything baked into the launches changed
+  gs_context::GraphKey k;
+  k.n = c->n; k.n_tiles = n_tiles; k.cap_inst = c->cap_inst; k.p0 = c->depth; k.p1 = c->inst_rec; k.p2 = c->center_scale;
+  if (memcmp(&k, &c->gkey, sizeof(k)) != 0) {
+    drop_graphs(c);
+    c->gkey = k;
+  }
+  if (c->use_graphs) {
+    cudaGraphExec_t &ge = sl.graph[reuse ? 1 : 0];
+    if (!ge) {
+      cudaGraph_t g = nullptr;
+      GS_CUDA(c, cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+      cudaError_t e = enqueue_frame(c, sl, reuse, n_tiles, true);
+      cudaError_t e2 = cudaStreamEndCapture(c->stream, &g);
+      if (e != cudaSuccess || e2 != cudaSuccess || !g) {
+        if (g) cudaGraphDestroy(g);
+        cudaGetLastError();
+        c->use_graphs = false;  // fall back to plain launches for the rest of this context's life
+      } else {
+        e = cudaGraphInstantiate(&ge, g, 0);
+        cudaGraphDestroy(g);
+        if (e != cudaSuccess) { ge = nullptr; cudaGetLastError(); c->use_graphs = false; }
+      }
+    }
+    if (ge) {
+      GS_CUDA(c, cudaGraphLaunch(ge, c->stream));
+      return GS_OK;
+    }
+  }
+  GS_CUDA(c, enqueue_frame(c, sl, reuse, n_tiles, false));
+  return GS_OK;
+}
+
+// after the frame's kernels: counters (and the frame, when the caller's buffer is host memory) go to the host on
+// the copy stream, so the next frame's kernels overlap the PCIe transfer
+static int enqueue_readback(gs_context *c, gs_context::Slot &sl) {
+  GS_CUDA(c, cudaEventRecord(sl.ev_done, c->stream));
+  GS_CUDA(c, cudaStreamWaitEvent(c->copy_stream, sl.ev_done, 0));
+  GS_CUDA(c, cudaMemcpyAsync(sl.ctr_host, sl.ctr, sizeof(FrameCounters), cudaMemcpyDeviceToHost, c->copy_stream));
+  if (sl.host_out)
+    GS_CUDA(c, cudaMemcpyAsync(sl.out_user, sl.frame_dev, sl.out_bytes, cudaMemcpyDeviceToHost, c->copy_stream));
+  GS_CUDA(c, cudaEventRecord(sl.ev_copied, c->copy_stream));
+  return GS_OK;
+}
+
+static int submit(gs_context *c, gs_context::Slot &sl) {
+  const gs_render_params *p = &sl.params;
+  FrameParams &fp = *sl.fp_host;
+  RenderConsts &rc = fp.rc;
+  memset(&fp, 0, sizeof(fp));
   memcpy(rc.proj, p->proj, sizeof(rc.proj));
   memcpy(rc.mv, p->modelview, sizeof(rc.mv));
   rc.width = p->width;
@@ -367,95 +483,111 @@ extern "C" int gs_render(gs_context *c, const gs_render_params *p, void *out_rgb
   rc.tiles_x = (p->width + kTile - 1) / kTile;
   rc.tiles_y = (p->height + kTile - 1) / kTile;
   rc.n_tiles = rc.tiles_x * rc.tiles_y;
-  if (rc.n_tiles >= 0xFFFFu) return fail(c, GS_ERR_INVALID, "more than 65534 tiles");
   memcpy(rc.bg, p->bg_rgba, sizeof(rc.bg));
   rc.shard_rank = c->shard_rank;
   rc.shard_world = c->shard_world;
   rc.out_format = p->out_format;
   rc.out_tiled = (p->flags & GS_RENDER_OUT_TILED) ? 1u : 0u;
+  const float view[4] = {p->modelview[2], p->modelview[6], p->modelview[10], p->modelview[14]};  // index.js:442
+  fill_sort_consts(fp.sc, view, p->has_cutout ? p->cutout16 : nullptr);
 
-  const bool reuse = (p->flags & GS_RENDER_REUSE_SORT) && c->have_order;
-  int rcode = ensure_scratch(c);
-  if (rcode) return rcode;
-  if ((rcode = ensure_tiles(c, rc.n_tiles))) return rcode;
-  if (c->cap_inst == 0) {
-    if ((rcode = ensure_instances(c, std::max<uint64_t>(1u << 20, (uint64_t)c->n * 4)))) return rcode;
-  }
+  int rcode;
   const size_t px_bytes = p->out_format == GS_FORMAT_RGBA8 ? 4 : 16;
   size_t out_pixels = (size_t)p->width * p->height;
   if (rc.out_tiled) out_pixels = (size_t)gs_owned_tiles(p->width, p->height, c->shard_rank, c->shard_world) * 256;
-  const size_t out_bytes = out_pixels * px_bytes;
-  void *out_dev = out_rgba;
-  if (!(p->flags & GS_RENDER_OUT_DEVICE)) {
-    if ((rcode = ensure_frame(c, out_bytes))) return rcode;
-    out_dev = c->frame_dev;
+  sl.out_bytes = out_pixels * px_bytes;
+  sl.host_out = !(p->flags & GS_RENDER_OUT_DEVICE);
+  if (sl.host_out) {
+    if ((rcode = ensure_frame(c, sl, sl.out_bytes))) return rcode;
+    fp.out = sl.frame_dev;
+  } else {
+    fp.out = sl.out_user;
   }
-
-  SortConsts sc;
-  const float view[4] = {p->modelview[2], p->modelview[6], p->modelview[10], p->modelview[14]};  // index.js:442
-  fill_sort_consts(sc, view, p->has_cutout ? p->cutout16 : nullptr);
-
-  // header of FrameCounters preserved across frames when the previous order is reused
-  struct SortHeader { unsigned long long min_enc, max_enc; uint32_t n_valid, n_inrange, n_dropped; };
-  SortHeader keep{};
-  if (reuse) {
-    keep.min_enc = c->counters_host->min_enc; keep.max_enc = c->counters_host->max_enc;
-    keep.n_valid = c->counters_host->n_valid; keep.n_inrange = c->counters_host->n_inrange;
-    keep.n_dropped = c->counters_host->n_dropped;
-  }
-
-  for (int attempt = 0; attempt < 8; ++attempt) {
-    uint32_t launches = 0;
-    GS_CUDA(c, cudaMemsetAsync(c->counters, 0, sizeof(FrameCounters), c->stream));
-    GS_CUDA(c, cudaMemsetAsync(c->tile_count, 0, sizeof(uint32_t) * ((size_t)rc.n_tiles + 1), c->stream));
-    GS_CUDA(c, cudaEventRecord(c->ev[0], c->stream));
-    if (reuse) {
-      GS_CUDA(c, cudaMemcpyAsync(&c->counters->min_enc, &keep.min_enc, 16, cudaMemcpyHostToDevice, c->stream));
-      GS_CUDA(c, cudaMemcpyAsync(&c->counters->n_valid, &keep.n_valid, 12, cudaMemcpyHostToDevice, c->stream));
-    } else {
-      launches += enqueue_sort(c, sc);
-    }
-    GS_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
-    launch_project(c, rc);
-    launches += 1;
-    GS_CUDA(c, cudaEventRecord(c->ev[2], c->stream));
-    launch_emit(c, rc);
-    launch_tile_radix(c);
-    launch_tile_scan(c, rc);
-    launches += 9;
-    GS_CUDA(c, cudaEventRecord(c->ev[3], c->stream));
-    launch_raster(c, rc, out_dev);
-    launches += 1;
-    GS_CUDA(c, cudaEventRecord(c->ev[4], c->stream));
-    GS_CUDA(c, cudaGetLastError());
-    GS_CUDA(c, cudaMemcpyAsync(c->counters_host, c->counters, sizeof(FrameCounters), cudaMemcpyDeviceToHost, c->stream));
-    if (!(p->flags & GS_RENDER_OUT_DEVICE))
-      GS_CUDA(c, cudaMemcpyAsync(out_rgba, out_dev, out_bytes, cudaMemcpyDeviceToHost, c->stream));
-    GS_CUDA(c, cudaStreamSynchronize(c->stream));
-    c->stats.kernel_launches = launches;
-    if (!c->counters_host->overflow) break;
-    // instance buffer too small: grow to the measured demand and run the frame again
-    const uint64_t need = std::max<uint64_t>(c->counters_host->n_inst + c->counters_host->n_inst / 8, c->cap_inst * 2);
-    if ((rcode = ensure_instances(c, need))) return rcode;
-    if (attempt == 7) return fail(c, GS_ERR_CAPACITY, "instance buffer kept overflowing");
-  }
-
-  const uint32_t launches = c->stats.kernel_launches;
-  memset(&c->stats, 0, sizeof(c->stats));
-  stats_from_counters(c);
-  c->stats.kernel_launches = launches;
-  c->stats.n_tiles = rc.n_tiles;
-  c->stats.width = p->width;
-  c->stats.height = p->height;
-  cudaEventElapsedTime(&c->stats.ms_sort, c->ev[0], c->ev[1]);
-  cudaEventElapsedTime(&c->stats.ms_project, c->ev[1], c->ev[2]);
-  cudaEventElapsedTime(&c->stats.ms_bin, c->ev[2], c->ev[3]);
-  cudaEventElapsedTime(&c->stats.ms_raster, c->ev[3], c->ev[4]);
-  cudaEventElapsedTime(&c->stats.ms_total, c->ev[0], c->ev[4]);
+  const bool reuse = (p->flags & GS_RENDER_REUSE_SORT) && c->have_order;
+  if ((rcode = launch_frame(c, sl, reuse, rc.n_tiles))) return rcode;
+  if ((rcode = enqueue_readback(c, sl))) return rcode;
+  sl.pending = true;
   c->have_order = true;
-  c->order_count = c->counters_host->n_valid;
+  return GS_OK;
+}
+
+static int wait_slot(gs_context *c, gs_context::Slot &sl, gs_stats *stats) {
+  if (!sl.pending) return fail(c, GS_ERR_INVALID, "gs_wait: no frame in flight for this ticket");
+  for (int attempt = 0;; ++attempt) {
+    GS_CUDA(c, cudaEventSynchronize(sl.ev_copied));
+    sl.pending = false;
+    if (!sl.ctr_host->overflow) break;
+    if (attempt == 7) return fail(c, GS_ERR_CAPACITY, "instance buffer kept overflowing");
+    // instance buffer too small: grow to the measured demand and run this frame again
+    const uint64_t need = std::max<uint64_t>(sl.ctr_host->n_inst + sl.ctr_host->n_inst / 8, c->cap_inst * 2);
+    GS_CUDA(c, cudaStreamSynchronize(c->stream));  // the other slot's frame may still be using the buffers
+    int rcode = ensure_instances(c, need);
+    if (rcode) return rcode;
+    if ((rcode = submit(c, sl))) return rcode;
+  }
+  memset(&c->stats, 0, sizeof(c->stats));
+  stats_from_counters(c, *sl.ctr_host);
+  c->stats.kernel_launches = sl.launches;
+  c->stats.n_tiles = sl.fp_host->rc.n_tiles;
+  c->stats.width = sl.params.width;
+  c->stats.height = sl.params.height;
+  cudaEventElapsedTime(&c->stats.ms_sort, sl.ev[0], sl.ev[1]);
+  cudaEventElapsedTime(&c->stats.ms_project, sl.ev[1], sl.ev[2]);
+  cudaEventElapsedTime(&c->stats.ms_bin, sl.ev[2], sl.ev[3]);
+  cudaEventElapsedTime(&c->stats.ms_raster, sl.ev[3], sl.ev[4]);
+  cudaEventElapsedTime(&c->stats.ms_total, sl.ev[0], sl.ev[4]);
+  c->order_count = sl.ctr_host->n_valid;
   if (stats) *stats = c->stats;
   return GS_OK;
+}
+
+extern "C" int gs_render_async(gs_context *c, const gs_render_params *p, void *out_rgba, uint64_t *out_ticket) {
+  if (!c || !p || !out_rgba) return GS_ERR_INVALID;
+  if (c->n == 0) return fail(c, GS_ERR_EMPTY, "gs_render before any push");
+  if (p->width == 0 || p->height == 0 || p->width > 4096 || p->height > 4096)
+    return fail(c, GS_ERR_INVALID, "frame size must be within 1..4096 per side");
+  if (p->out_format != GS_FORMAT_RGBA8 && p->out_format != GS_FORMAT_RGBA32F) return fail(c, GS_ERR_INVALID, "bad out_format");
+  const uint32_t n_tiles = ((p->width + kTile - 1) / kTile) * ((p->height + kTile - 1) / kTile);
+  if (n_tiles >= 0xFFFFu) return fail(c, GS_ERR_INVALID, "more than 65534 tiles");
+  GS_CUDA(c, cudaSetDevice(c->device));
+  const uint64_t ticket = c->next_ticket;
+  gs_context::Slot &sl = c->slot[ticket & 1];
+  int rcode;
+  if (sl.pending && (rcode = wait_slot(c, sl, nullptr))) return rcode;  // slot reuse: its previous frame must be done
+  // growing any shared buffer needs an idle pipeline
+  const bool grow = !(c->scratch_cap >= c->cap && c->depth) || !(n_tiles <= c->tiles_cap && c->tile_count) || c->cap_inst == 0;
+  if (grow) {
+    if ((rcode = drain(c))) return rcode;
+    GS_CUDA(c, cudaStreamSynchronize(c->stream));
+    if ((rcode = ensure_scratch(c))) return rcode;
+    if ((rcode = ensure_tiles(c, n_tiles))) return rcode;
+    if (c->cap_inst == 0 && (rcode = ensure_instances(c, std::max<uint64_t>(1u << 20, (uint64_t)c->n * 4)))) return rcode;
+  }
+  sl.params = *p;
+  sl.out_user = out_rgba;
+  if ((rcode = submit(c, sl))) return rcode;
+  c->next_ticket = ticket + 1;
+  if (out_ticket) *out_ticket = ticket;
+  return GS_OK;
+}
+
+extern "C" int gs_wait(gs_context *c, uint64_t ticket, gs_stats *stats) {
+  if (!c) return GS_ERR_INVALID;
+  if (ticket >= c->next_ticket) return fail(c, GS_ERR_INVALID, "gs_wait: unknown ticket");
+  GS_CUDA(c, cudaSetDevice(c->device));
+  gs_context::Slot &sl = c->slot[ticket & 1];
+  if (ticket + 2 < c->next_ticket || !sl.pending) {  // already completed (e.g. by a slot-reuse wait): stats of that frame are gone, frame is in place
+    if (stats) *stats = c->stats;
+    return GS_OK;
+  }
+  return wait_slot(c, sl, stats);
+}
+
+extern "C" int gs_render(gs_context *c, const gs_render_params *p, void *out_rgba, gs_stats *stats) {
+  uint64_t t = 0;
+  int rc = gs_render_async(c, p, out_rgba, &t);
+  if (rc) return rc;
+  return gs_wait(c, t, stats);
 }
 
 extern "C" int gs_get_stats(const gs_context *c, gs_stats *out) {
@@ -486,8 +618,7 @@ extern "C" int gs_assemble_tiles(gs_context *c, const void *gathered, uint32_t t
   if (!c || !gathered || !out_frame || world == 0) return GS_ERR_INVALID;
   GS_CUDA(c, cudaSetDevice(c->device));
   launch_assemble(c, gathered, tiles_per_rank, world, width, height, format, out_frame);
-  GS_CUDA(c, cudaGetLastError());
-  GS_CUDA(c, cudaStreamSynchronize(c->stream));
+  GS_CUDA(c, cudaGetLastError());  // stream-ordered: complete after gs_synchronize / any later stream work
   return GS_OK;
 }
 

@@ -69,6 +69,20 @@ struct SortConsts {
   int has_cutout;
 };
 
+// Per-frame inputs, resident in device memory (one copy per pipeline slot) so that the whole frame is a static
+// CUDA graph: a 400-byte host->device copy of this struct is the only per-frame input traffic.
+struct FrameParams {
+  SortConsts sc;
+  RenderConsts rc;
+  void *out;  // frame (or packed owned tiles) destination of the raster
+};
+
+// preserved part of FrameCounters when a frame reuses the previous draw order
+struct SortHeader {
+  unsigned long long min_enc, max_enc;
+  uint32_t n_valid, n_inrange, n_dropped, pad;
+};
+
 }  // namespace gs
 
 struct gs_context {
@@ -110,39 +124,52 @@ struct gs_context {
   uint32_t tiles_cap = 0;
   uint32_t *tile_count = nullptr;  // [T]
   uint32_t *tile_start = nullptr;  // [T+1]
-  gs::FrameCounters *counters = nullptr;     // device
-  gs::FrameCounters *counters_host = nullptr;  // pinned
   double *quirk_table = nullptr;   // parseInt quirk thresholds (device)
   int quirk_n = 0;
+  gs::SortHeader *sort_hdr = nullptr;  // device: counters header of the last sort (for GS_RENDER_REUSE_SORT)
 
-  // ---- frame buffer owned by the context (used when the caller passes host memory) ----
-  void *frame_dev = nullptr;
-  size_t frame_bytes = 0;
-  void *frame_pinned = nullptr;
-  size_t frame_pinned_bytes = 0;
+  // ---- two pipeline slots: frame k+1 is rasterised while frame k is copied to the host ----
+  struct Slot {
+    gs::FrameCounters *ctr = nullptr;        // device
+    gs::FrameCounters *ctr_host = nullptr;   // pinned
+    gs::FrameParams *fp = nullptr;           // device
+    gs::FrameParams *fp_host = nullptr;      // pinned staging
+    void *frame_dev = nullptr;               // used when the caller's buffer is host memory
+    size_t frame_bytes = 0;
+    cudaEvent_t ev[5]{};                     // stage boundaries (timing)
+    cudaEvent_t ev_done = nullptr, ev_copied = nullptr;
+    cudaGraphExec_t graph[2] = {nullptr, nullptr};  // [reuse_sort]
+    bool pending = false;
+    bool host_out = false;
+    void *out_user = nullptr;
+    size_t out_bytes = 0;
+    gs_render_params params{};
+    uint32_t launches = 0;
+  } slot[2];
+  uint64_t next_ticket = 0;
+  cudaStream_t copy_stream = nullptr;
+  bool use_graphs = true;
+  // graph cache key: anything baked into the captured launches
+  struct GraphKey { uint32_t n = 0, n_tiles = 0; uint64_t cap_inst = 0; const void *p0 = nullptr, *p1 = nullptr, *p2 = nullptr; } gkey;
 
   uint32_t shard_rank = 0, shard_world = 1;
   bool have_order = false;
   uint32_t order_count = 0;
   gs_stats stats{};
-  cudaEvent_t ev[8]{};
+  cudaEvent_t ev[2]{};  // gs_sort timing
 };
 
 namespace gs {
 
-// -- launchers (each .cu file owns its kernels) --
-// sort
-void launch_depth_cull(gs_context *c, const SortConsts &sc);
-void launch_depth_radix(gs_context *c);  // two passes -> c->order
-// pack
+// -- launchers (each .cu file owns its kernels); every per-frame input comes from device memory (fp, ctr) --
+void launch_depth_cull(gs_context *c, const FrameParams *fp, FrameCounters *ctr);
+void launch_depth_radix(gs_context *c, FrameCounters *ctr);  // 6 launches -> c->order
 void launch_pack(gs_context *c, const uint8_t *rows_dev, uint32_t first, uint32_t n);
-// project + bin
-void launch_project(gs_context *c, const RenderConsts &rc);
-void launch_emit(gs_context *c, const RenderConsts &rc);
-void launch_tile_radix(gs_context *c);
-void launch_tile_scan(gs_context *c, const RenderConsts &rc);
-// raster
-void launch_raster(gs_context *c, const RenderConsts &rc, void *out_dev);
+void launch_project(gs_context *c, const FrameParams *fp);
+void launch_emit(gs_context *c, const FrameParams *fp, FrameCounters *ctr);  // 2 launches
+void launch_tile_radix(gs_context *c, FrameCounters *ctr);                   // 6 launches
+void launch_tile_scan(gs_context *c, uint32_t n_tiles);
+void launch_raster(gs_context *c, const FrameParams *fp, uint32_t n_tiles);
 void launch_assemble(gs_context *c, const void *gathered, uint32_t tiles_per_rank, uint32_t world, uint32_t width,
                      uint32_t height, int32_t format, void *out_frame);
 
@@ -165,6 +192,22 @@ __host__ __device__ inline double dec_f64(unsigned long long e) {
   memcpy(&d, &u, 8);
   return d;
 #endif
+}
+
+// ---- multi-GPU tile ownership: rank r owns the tile COLUMNS tx with tx % world == r (16-pixel wide vertical
+// stripes, interleaved), so the owned tiles of any tile rectangle have a closed form ----
+__host__ __device__ inline uint32_t owned_cols(uint32_t tiles_x, uint32_t rank, uint32_t world) {
+  return rank < tiles_x ? (tiles_x - 1 - rank) / world + 1 : 0u;
+}
+// packed index of owned tile (tx, ty) in rank's tile buffer (row-major over its own columns)
+__host__ __device__ inline uint32_t owned_slot(uint32_t tx, uint32_t ty, uint32_t tiles_x, uint32_t rank, uint32_t world) {
+  return ty * owned_cols(tiles_x, rank, world) + (tx - rank) / world;
+}
+// first owned column >= tx0 and number of owned columns in [tx0, tx1]
+__host__ __device__ inline void owned_span(uint32_t tx0, uint32_t tx1, uint32_t rank, uint32_t world, uint32_t &first,
+                                           uint32_t &ncols) {
+  first = tx0 + (rank + world - tx0 % world) % world;
+  ncols = first <= tx1 ? (tx1 - first) / world + 1 : 0u;
 }
 
 __device__ __forceinline__ uint32_t ld_relaxed(const uint32_t *p) {

@@ -34,8 +34,10 @@ __device__ __forceinline__ void unpack_int16(uint32_t value, float &lo, float &h
 // the reference may draw through the zero tail of quirk Q5.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_project(const float4 *__restrict__ cs, const uint4 *__restrict__ cc,
-                                                 const float *__restrict__ depth, uint32_t n, RenderConsts rc,
-                                                 float4 *__restrict__ rec_out, uint32_t *__restrict__ rect_out) {
+                                                 const float *__restrict__ depth, uint32_t n,
+                                                 const FrameParams *__restrict__ fp, float4 *__restrict__ rec_out,
+                                                 uint32_t *__restrict__ rect_out) {
+  const RenderConsts &rc = fp->rc;
   const uint32_t stride = gridDim.x * blockDim.x;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     uint32_t rect = kNoRect;
@@ -140,10 +142,15 @@ __global__ void __launch_bounds__(256) k_project(const float4 *__restrict__ cs, 
   }
 }
 
-__device__ __forceinline__ uint32_t rect_count(uint32_t r) {
+// candidate tiles of a packed rectangle that this rank owns (all of them on one GPU)
+__device__ __forceinline__ uint32_t rect_count(uint32_t r, uint32_t rank, uint32_t world) {
   if (r == kNoRect) return 0u;
-  const uint32_t w = ((r >> 8) & 255u) - (r & 255u) + 1u;
   const uint32_t h = (r >> 24) - ((r >> 16) & 255u) + 1u;
+  uint32_t w = ((r >> 8) & 255u) - (r & 255u) + 1u;
+  if (world > 1) {
+    uint32_t first;
+    owned_span(r & 255u, (r >> 8) & 255u, rank, world, first, w);
+  }
   return w * h;
 }
 
@@ -152,7 +159,9 @@ __device__ __forceinline__ uint32_t rect_count(uint32_t r) {
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kEmitThreads) k_count(const uint32_t *__restrict__ order,
                                                         const uint32_t *__restrict__ rect,
-                                                        uint32_t *__restrict__ tile_total, FrameCounters *ctr) {
+                                                        uint32_t *__restrict__ tile_total, FrameCounters *ctr,
+                                                        const FrameParams *__restrict__ fp) {
+  const uint32_t shard_rank = fp->rc.shard_rank, shard_world = fp->rc.shard_world;
   __shared__ uint32_t s_sum[kEmitThreads / 32], s_vis[kEmitThreads / 32];
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t nv = ctr->n_valid;
@@ -165,7 +174,7 @@ __global__ void __launch_bounds__(kEmitThreads) k_count(const uint32_t *__restri
       const uint32_t j = j0 + k;
       if (j < nv) {
         const uint32_t r = __ldg(rect + __ldg(order + j));
-        sum += rect_count(r);
+        sum += rect_count(r, shard_rank, shard_world);
         vis += (r != kNoRect);
       }
     }
@@ -195,10 +204,11 @@ __global__ void __launch_bounds__(kEmitThreads) k_count(const uint32_t *__restri
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kEmitThreads, 6) k_emit(const uint32_t *__restrict__ order,
                                                        const uint32_t *__restrict__ rect,
-                                                       const float4 *__restrict__ proj_rec, RenderConsts rc,
-                                                       uint64_t cap_inst, const uint32_t *__restrict__ tile_total,
+                                                       const float4 *__restrict__ proj_rec,
+                                                       const FrameParams *__restrict__ fp, uint64_t cap_inst, const uint32_t *__restrict__ tile_total,
                                                        uint16_t *__restrict__ inst_tile, uint32_t *__restrict__ inst_idx,
                                                        uint32_t *__restrict__ tile_count, FrameCounters *ctr) {
+  const RenderConsts &rc = fp->rc;
   __shared__ uint32_t s_off[kEmitTile];
   __shared__ uint32_t s_rect[kEmitTile];
   __shared__ uint32_t s_idx[kEmitTile];
@@ -232,7 +242,7 @@ __global__ void __launch_bounds__(kEmitThreads, 6) k_emit(const uint32_t *__rest
       }
       s_idx[tid * kEmitItems + k] = idx;
       s_rect[tid * kEmitItems + k] = r;
-      cnt[k] = rect_count(r);
+      cnt[k] = rect_count(r, rc.shard_rank, rc.shard_world);
       sum += cnt[k];
     }
     uint32_t incl = sum;
@@ -255,7 +265,7 @@ __global__ void __launch_bounds__(kEmitThreads, 6) k_emit(const uint32_t *__rest
     __syncthreads();
     // ---- expansion: one thread per instance, strided over the slice's instance space (balanced whatever
     //      the rectangle sizes); the entry of instance e is found by binary search in the scanned offsets ----
-    const uint32_t total = s_off[kEmitTile - 1] + rect_count(s_rect[kEmitTile - 1]);
+    const uint32_t total = s_off[kEmitTile - 1] + rect_count(s_rect[kEmitTile - 1], rc.shard_rank, rc.shard_world);
     for (uint32_t e = tid; e < total; e += kEmitThreads) {
       uint32_t lo = 0, hi = kEmitTile;
 #pragma unroll
@@ -266,13 +276,20 @@ __global__ void __launch_bounds__(kEmitThreads, 6) k_emit(const uint32_t *__rest
       const uint32_t r = s_rect[lo];
       const uint32_t idx = s_idx[lo];
       const uint32_t k = e - s_off[lo];
-      const uint32_t tx0 = r & 255u, w = ((r >> 8) & 255u) - tx0 + 1u, ty0 = (r >> 16) & 255u;
-      const uint32_t n_t = w * ((r >> 24) - ty0 + 1u);
+      // owned columns of the rectangle: first, first + world, ... (all columns on one GPU)
+      uint32_t tx0 = r & 255u, w = ((r >> 8) & 255u) - tx0 + 1u;
+      const uint32_t ty0 = (r >> 16) & 255u;
+      const uint32_t n_all = w * ((r >> 24) - ty0 + 1u);
+      uint32_t step = 1u;
+      if (rc.shard_world > 1) {
+        owned_span(tx0, (r >> 8) & 255u, rc.shard_rank, rc.shard_world, tx0, w);
+        step = rc.shard_world;
+      }
       // k / w for k < 65536, w <= 256: float quotient of (k + 0.5) is never within rounding of an integer
       const uint32_t dy_t = (uint32_t)__fdividef((float)k + 0.5f, (float)w);
-      const uint32_t tx = tx0 + (k - dy_t * w), ty = ty0 + dy_t;
-      bool keep = (rc.shard_world <= 1) || (((tx + ty) % rc.shard_world) == rc.shard_rank);
-      if (keep && n_t > 1) {
+      const uint32_t tx = tx0 + (k - dy_t * w) * step, ty = ty0 + dy_t;
+      bool keep = true;
+      if (n_all > 1) {
         // footprint geometry: neighbouring instances share the splat, so these gathers mostly hit L1
         const float4 r0 = __ldg(proj_rec + 2 * (size_t)idx);                       // cx, cy, a1x, a1y
         const float2 r1 = __ldg((const float2 *)(proj_rec + 2 * (size_t)idx + 1));  // a2x, a2y
@@ -342,26 +359,26 @@ __global__ void __launch_bounds__(1024) k_tile_scan(const uint32_t *__restrict__
   if (tid == 0) tile_start[n_tiles] = s_carry;
 }
 
-void launch_project(gs_context *c, const RenderConsts &rc) {
+void launch_project(gs_context *c, const FrameParams *fp) {
   uint64_t blocks = ((uint64_t)c->n + 255) / 256;
   const uint64_t cap = (uint64_t)c->sm_count * 16;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
-  k_project<<<(int)blocks, 256, 0, c->stream>>>(c->center_scale, c->cov_color, c->depth, c->n, rc, c->proj_rec, c->rect);
+  k_project<<<(int)blocks, 256, 0, c->stream>>>(c->center_scale, c->cov_color, c->depth, c->n, fp, c->proj_rec, c->rect);
 }
 
-void launch_emit(gs_context *c, const RenderConsts &rc) {
+void launch_emit(gs_context *c, const FrameParams *fp, FrameCounters *ctr) {
   uint64_t tiles = ((uint64_t)c->n + kEmitTile - 1) / kEmitTile;
   const uint64_t cap = (uint64_t)c->sm_count * 8;
   if (tiles > cap) tiles = cap;
   if (tiles < 1) tiles = 1;
-  k_count<<<(int)tiles, kEmitThreads, 0, c->stream>>>(c->order, c->rect, c->tile_total, c->counters);
-  k_emit<<<(int)tiles, kEmitThreads, 0, c->stream>>>(c->order, c->rect, c->proj_rec, rc, c->cap_inst, c->tile_total,
-                                                     c->inst_tile, c->inst_idx, c->tile_count, c->counters);
+  k_count<<<(int)tiles, kEmitThreads, 0, c->stream>>>(c->order, c->rect, c->tile_total, ctr, fp);
+  k_emit<<<(int)tiles, kEmitThreads, 0, c->stream>>>(c->order, c->rect, c->proj_rec, fp, c->cap_inst, c->tile_total,
+                                                     c->inst_tile, c->inst_idx, c->tile_count, ctr);
 }
 
-void launch_tile_scan(gs_context *c, const RenderConsts &rc) {
-  k_tile_scan<<<1, 1024, 0, c->stream>>>(c->tile_count, rc.n_tiles, c->tile_start);
+void launch_tile_scan(gs_context *c, uint32_t n_tiles) {
+  k_tile_scan<<<1, 1024, 0, c->stream>>>(c->tile_count, n_tiles, c->tile_start);
 }
 
 }  // namespace gs

@@ -51,37 +51,23 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
   }
 }
 
-// index (within rank `rank`'s packed tile list) of tile (tx, ty); tiles are owned when (tx+ty)%world==rank
-__host__ __device__ inline uint32_t owned_in_row(uint32_t tiles_x, uint32_t ty, uint32_t upto_x, uint32_t rank,
-                                                 uint32_t world) {
-  // number of tx in [0, upto_x) with (tx + ty) % world == rank
-  const uint32_t r0 = (rank + world - (ty % world)) % world;
-  (void)tiles_x;
-  return upto_x > r0 ? (upto_x - 1 - r0) / world + 1 : 0u;
-}
-__host__ __device__ inline uint32_t owned_slot(uint32_t tx, uint32_t ty, uint32_t tiles_x, uint32_t rank,
-                                               uint32_t world) {
-  // every `world` consecutive rows own exactly tiles_x tiles between them
-  uint32_t slot = (ty / world) * tiles_x;
-  for (uint32_t y = (ty / world) * world; y < ty; ++y) slot += owned_in_row(tiles_x, y, tiles_x, rank, world);
-  return slot + owned_in_row(tiles_x, ty, tx, rank, world);
-}
-
 __device__ __forceinline__ uint32_t to_u8(float v) {
   v = fminf(fmaxf(v, 0.0f), 1.0f);
   return (uint32_t)(v * 255.0f + 0.5f);
 }
 
 __global__ void __launch_bounds__(256) k_raster(const float4 *__restrict__ inst_rec,
-                                                const uint32_t *__restrict__ tile_start, RenderConsts rc,
-                                                void *__restrict__ out) {
+                                                const uint32_t *__restrict__ tile_start,
+                                                const FrameParams *__restrict__ fp) {
+  const RenderConsts &rc = fp->rc;
+  void *out = fp->out;
   __shared__ __align__(128) float4 s_rec[kStages][kChunk * 2];
   __shared__ __align__(16) float4 s_col[kChunk];
   __shared__ __align__(8) uint64_t s_full[kStages];
 
   const uint32_t tile = blockIdx.x;
   const uint32_t tx = tile % rc.tiles_x, ty = tile / rc.tiles_x;
-  if (rc.shard_world > 1 && ((tx + ty) % rc.shard_world) != rc.shard_rank) return;
+  if (rc.shard_world > 1 && (tx % rc.shard_world) != rc.shard_rank) return;
 
   const uint32_t tid = threadIdx.x;
   const uint32_t lx = tid & 15u, ly = tid >> 4;
@@ -192,7 +178,7 @@ __global__ void __launch_bounds__(256) k_assemble(const void *__restrict__ gathe
   const uint32_t tid = threadIdx.x;
   const uint32_t x = tx * kTile + (tid & 15u), y = ty * kTile + (tid >> 4);
   if (x >= width || y >= height) return;
-  const uint32_t rank = (tx + ty) % world;
+  const uint32_t rank = tx % world;
   const uint32_t slot = (world > 1) ? owned_slot(tx, ty, tiles_x, rank, world) : tile;
   const size_t src = ((size_t)rank * tiles_per_rank + slot) * 256 + tid;
   const size_t dst = (size_t)y * width + x;
@@ -200,8 +186,8 @@ __global__ void __launch_bounds__(256) k_assemble(const void *__restrict__ gathe
   else ((float4 *)out)[dst] = ((const float4 *)gathered)[src];
 }
 
-void launch_raster(gs_context *c, const RenderConsts &rc, void *out_dev) {
-  k_raster<<<rc.n_tiles, 256, 0, c->stream>>>(c->inst_rec, c->tile_start, rc, out_dev);
+void launch_raster(gs_context *c, const FrameParams *fp, uint32_t n_tiles) {
+  k_raster<<<n_tiles, 256, 0, c->stream>>>(c->inst_rec, c->tile_start, fp);
 }
 
 void launch_assemble(gs_context *c, const void *gathered, uint32_t tiles_per_rank, uint32_t world, uint32_t width,
@@ -214,7 +200,7 @@ uint32_t owned_tiles_host(uint32_t width, uint32_t height, uint32_t rank, uint32
   const uint32_t tiles_x = (width + kTile - 1) / kTile, tiles_y = (height + kTile - 1) / kTile;
   if (world <= 1) return tiles_x * tiles_y;
   uint32_t n = 0;
-  for (uint32_t y = 0; y < tiles_y; ++y) n += owned_in_row(tiles_x, y, tiles_x, rank, world);
+  n = tiles_y * owned_cols(tiles_x, rank, world);
   return n;
 }
 

@@ -44,8 +44,9 @@ __device__ __forceinline__ DepthRange load_depth_range(const FrameCounters *ctr)
 // K1: depth + cull + min/max (index.js:517-555).  Reads 16 B + 4 B per splat, writes 4 B.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_depth_cull(const float4 *__restrict__ cs, const float *__restrict__ sa,
-                                                    uint32_t n, SortConsts sc, float *__restrict__ depth_out,
-                                                    FrameCounters *ctr) {
+                                                    uint32_t n, const FrameParams *__restrict__ fp,
+                                                    float *__restrict__ depth_out, FrameCounters *ctr) {
+  const SortConsts sc = fp->sc;
   double dmin = INFINITY, dmax = -INFINITY;
   uint32_t cnt = 0;
   const uint32_t stride = gridDim.x * blockDim.x;
@@ -396,14 +397,14 @@ static int persistent_grid(gs_context *c, uint64_t n_elems, int per_cta, int cta
   return (int)(tiles < cap ? tiles : cap);
 }
 
-void launch_depth_cull(gs_context *c, const SortConsts &sc) {
+void launch_depth_cull(gs_context *c, const FrameParams *fp, FrameCounters *ctr) {
   const int grid = persistent_grid(c, c->n, 256 * 4, 8);
-  k_depth_cull<<<grid, 256, 0, c->stream>>>(c->center_scale, c->size_alpha, c->n, sc, c->depth, c->counters);
+  k_depth_cull<<<grid, 256, 0, c->stream>>>(c->center_scale, c->size_alpha, c->n, fp, c->depth, ctr);
 }
 
-static RadixArgs make_args(gs_context *c) {
+static RadixArgs make_args(gs_context *c, FrameCounters *ctr) {
   RadixArgs a{};
-  a.ctr = c->counters;
+  a.ctr = ctr;
   a.n_host = c->n;
   a.depth = c->depth;
   a.idx_a = c->idx_a;
@@ -427,8 +428,8 @@ static void run_pass(gs_context *c, RadixArgs &a, uint64_t n_max) {
 }
 
 // index.js:557-567 as two stable 8-bit passes -> c->order (6 launches)
-void launch_depth_radix(gs_context *c) {
-  RadixArgs a = make_args(c);
+void launch_depth_radix(gs_context *c, FrameCounters *ctr) {
+  RadixArgs a = make_args(c, ctr);
   a.table = c->table_n;
   a.totals = c->totals;
   a.stride = c->table_n_stride;
@@ -437,8 +438,8 @@ void launch_depth_radix(gs_context *c) {
 }
 
 // stable sort of the tile instances by tile id (6 launches); T2 writes the per-tile record lists
-void launch_tile_radix(gs_context *c) {
-  RadixArgs a = make_args(c);
+void launch_tile_radix(gs_context *c, FrameCounters *ctr) {
+  RadixArgs a = make_args(c, ctr);
   a.table = c->table_d;
   a.totals = c->totals + 256;
   a.stride = c->table_d_stride;

@@ -1,7 +1,7 @@
 """Multi-GPU frame sharding: one process per GPU, torch.distributed for the plumbing.
 
 The reference has no multi-GPU path (one worker + one GL context).  Here the FRAME is sharded, not the splat
-table: rank r rasters the 16x16 tiles with (tx + ty) % world == r.  Every rank keeps the full 36 B/splat table
+table: rank r rasters the 16x16 tile columns with tx % world == r.  Every rank keeps the full 36 B/splat table
 in its own HBM (80 M splats = 2.9 GB of 180 GB) and computes the same global draw order, so every pixel is
 composited on exactly one GPU in exactly the reference's order - the sharded frame is bit-identical to the
 single-GPU frame.  The only exchange step is one all-gather of finished RGBA tiles per frame
@@ -35,22 +35,18 @@ class TileSharding:
         return (self.height + TILE - 1) // TILE
 
     def owner(self, tx: int, ty: int) -> int:
-        return (tx + ty) % self.world
+        """rank r owns the tile COLUMNS tx with tx % world == r (csrc/gs_common.cuh owned_cols / owned_slot)"""
+        return tx % self.world
 
-    def owned_in_row(self, ty: int, upto_x: int, rank: int) -> int:
-        """tiles tx in [0, upto_x) of row ty owned by `rank` (mirrors csrc/gs_raster.cu owned_in_row)."""
-        r0 = (rank + self.world - (ty % self.world)) % self.world
-        return (upto_x - 1 - r0) // self.world + 1 if upto_x > r0 else 0
+    def owned_cols(self, rank: int) -> int:
+        return (self.tiles_x - 1 - rank) // self.world + 1 if rank < self.tiles_x else 0
 
     def slot(self, tx: int, ty: int, rank: int) -> int:
         """index of tile (tx, ty) inside rank's packed tile buffer (mirrors owned_slot)."""
-        base = (ty // self.world) * self.tiles_x
-        for y in range((ty // self.world) * self.world, ty):
-            base += self.owned_in_row(y, self.tiles_x, rank)
-        return base + self.owned_in_row(ty, tx, rank)
+        return ty * self.owned_cols(rank) + (tx - rank) // self.world
 
     def owned_tiles(self, rank: int) -> int:
-        return sum(self.owned_in_row(y, self.tiles_x, rank) for y in range(self.tiles_y))
+        return self.tiles_y * self.owned_cols(rank)
 
     @property
     def tiles_per_rank(self) -> int:
@@ -132,6 +128,7 @@ def make_gpu_sharded_renderer(ctx, frame_like, rank: int, world: int, fmt: int =
         torch.cuda.current_stream(dev).synchronize()
         dst = frame if out is None else out
         ctx.assemble_tiles(gathered.data_ptr(), sh.tiles_per_rank, world, w, h, fmt, dst.data_ptr())
+        ctx.synchronize()  # gs_assemble_tiles is stream-ordered
         return dst
 
     return ShardedRenderer(sh, rank, render_tiles, assemble, process_group), frame

@@ -135,6 +135,19 @@ class SplatContext:
         self.last_stats = st
         return st
 
+    def render_async(self, params: GsRenderParams, out_ptr: int) -> int:
+        """gs_render_async: enqueue one frame, return its ticket (two frames may be in flight)."""
+        t = C.c_uint64()
+        self._check(self._lib.gs_render_async(self._h, C.byref(params), C.c_void_p(out_ptr), C.byref(t)))
+        return t.value
+
+    def wait(self, ticket: int) -> GsStats:
+        """gs_wait: block until the frame of `ticket` (and its counters) are on the host."""
+        st = GsStats()
+        self._check(self._lib.gs_wait(self._h, ticket, C.byref(st)))
+        self.last_stats = st
+        return st
+
     def read_projected(self, first: int = 0, n: Optional[int] = None) -> np.ndarray:
         n = self.num_splats - first if n is None else n
         out = np.empty((n, 8), np.float32)

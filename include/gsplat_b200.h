@@ -147,6 +147,17 @@ typedef struct gs_render_params {
  */
 GS_API int gs_render(gs_context *ctx, const gs_render_params *params, void *out_rgba, gs_stats *stats);
 
+/*
+ * Pipelined form of gs_render (= gs_render_async + gs_wait).  gs_render_async enqueues the frame (one CUDA graph
+ * launch on the context's stream; the RGBA frame and the counters are then copied to the host on a second stream)
+ * and returns a ticket at once; gs_wait blocks until that frame is in out_rgba.  Two frames may be in flight, so
+ * the device renders frame k+1 while frame k crosses PCIe (the reference likewise overlaps its worker sort with
+ * drawing, index.js:206,439-440).  out_rgba must stay valid until gs_wait; use page-locked memory (gs_host_alloc)
+ * for a truly asynchronous copy.  A third gs_render_async waits for the oldest frame first.
+ */
+GS_API int gs_render_async(gs_context *ctx, const gs_render_params *params, void *out_rgba, uint64_t *out_ticket);
+GS_API int gs_wait(gs_context *ctx, uint64_t ticket, gs_stats *stats);
+
 /* Per-splat projected record of the last gs_render (testing the vertex-shader restatement):
  * 8 floats per resident splat {cx, cy, a1x, a1y, a2x, a2y, rgba8-as-bits, tile-rect-as-bits};
  * rect == 0xFFFFFFFF marks a splat that was not projected/visible. */
@@ -158,7 +169,7 @@ GS_API int gs_get_stats(const gs_context *ctx, gs_stats *out);
 
 /*
  * Shard the FRAME, not the splat table: rank r of `world` rasters the 16x16 tiles t with
- * (tx + ty) % world == r.  Every rank holds the full splat table (32 B/splat) and computes the
+ * tx % world == r (interleaved 16-pixel tile columns).  Every rank holds the full splat table (32 B/splat) and computes the
  * same global draw order, so each pixel is composited on exactly one GPU in exactly the
  * reference order.  The only exchange is an all-gather of finished RGBA tiles.
  */
@@ -166,7 +177,7 @@ GS_API int gs_set_shard(gs_context *ctx, uint32_t rank, uint32_t world);
 /* Number of tiles rank `rank` owns for a width x height frame (all ranks pad to the max). */
 GS_API uint32_t gs_owned_tiles(uint32_t width, uint32_t height, uint32_t rank, uint32_t world);
 /* Scatter `world` gathered tiled buffers (each tiles_per_rank*256 pixels) into a row-major frame.
- * gathered / out_frame are device pointers. */
+ * gathered / out_frame are device pointers.  Stream-ordered on gs_stream(ctx); call gs_synchronize to wait. */
 GS_API int gs_assemble_tiles(gs_context *ctx, const void *gathered, uint32_t tiles_per_rank, uint32_t world,
                              uint32_t width, uint32_t height, int32_t format, void *out_frame);
 

@@ -98,6 +98,7 @@ def test_gpu_sharded_equals_unsharded(gs, orc, ctx, world, fmt):
             host_tiles.append(t.view(dt).reshape(tpr, 256, 4))
         ctx.set_shard(0, 1)
         ctx.assemble_tiles(gathered, tpr, world, fr.width, fr.height, f, frame_dev)
+        ctx.synchronize()
         got = np.empty((fr.height, fr.width, 4), dt)
         ctx.memcpy_d2h(got, frame_dev, got.nbytes)
         assert np.array_equal(got, ref)  # bit-identical: each pixel is composited on exactly one rank
