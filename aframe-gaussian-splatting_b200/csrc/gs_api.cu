@@ -81,6 +81,7 @@ static int ensure_scratch(gs_context *c) {
   if (c->scratch_cap >= c->cap && c->depth) return GS_OK;
   dev_free(c->depth); dev_free(c->idx_a); dev_free(c->dig_a); dev_free(c->order);
   dev_free(c->proj_rec); dev_free(c->rect); dev_free(c->table_n); dev_free(c->tile_total);
+  dev_free(c->slice_prefix); dev_free(c->ent); dev_free(c->ent_off);
   const size_t n = c->cap;
   GS_CUDA(c, dev_alloc(&c->depth, n));
   GS_CUDA(c, dev_alloc(&c->idx_a, n));
@@ -91,6 +92,9 @@ static int ensure_scratch(gs_context *c) {
   c->table_n_stride = (uint32_t)((n + kRadixTile - 1) / kRadixTile + 1);
   GS_CUDA(c, dev_alloc(&c->table_n, (size_t)256 * c->table_n_stride));
   GS_CUDA(c, dev_alloc(&c->tile_total, (n + kEmitTile - 1) / kEmitTile + 1));
+  GS_CUDA(c, dev_alloc(&c->slice_prefix, (n + kEmitTile - 1) / kEmitTile + 2));
+  GS_CUDA(c, dev_alloc(&c->ent, n));
+  GS_CUDA(c, dev_alloc(&c->ent_off, n));
   c->scratch_cap = c->cap;
   c->have_order = false;
   return GS_OK;
@@ -177,10 +181,17 @@ extern "C" int gs_create(int device_ordinal, gs_context **out_ctx) {
   if ((e = cudaSetDevice(device_ordinal)) != cudaSuccess) return bail("cudaSetDevice", e);
   if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
   if ((e = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+  if ((e = cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+  for (int i = 0; i < 2; ++i) {
+    if ((e = cudaEventCreateWithFlags(&c->ev_fork[i], cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
+    if ((e = cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
+  }
   for (auto &ev : c->ev)
     if ((e = cudaEventCreate(&ev)) != cudaSuccess) return bail("cudaEventCreate", e);
   for (auto &sl : c->slot) {
     for (auto &ev : sl.ev)
+      if ((e = cudaEventCreate(&ev)) != cudaSuccess) return bail("cudaEventCreate", e);
+    for (auto &ev : sl.evp)
       if ((e = cudaEventCreate(&ev)) != cudaSuccess) return bail("cudaEventCreate", e);
     if ((e = cudaEventCreateWithFlags(&sl.ev_done, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
     if ((e = cudaEventCreateWithFlags(&sl.ev_copied, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
@@ -219,17 +230,24 @@ extern "C" int gs_destroy(gs_context *c) {
   if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
   drop_graphs(c);
   dev_free(c->table_n); dev_free(c->table_d); dev_free(c->tile_total); dev_free(c->totals); dev_free(c->sort_hdr);
+  dev_free(c->slice_prefix); dev_free(c->ent); dev_free(c->ent_off);
   for (auto &sl : c->slot) {
     dev_free(sl.ctr); dev_free(sl.fp);
     if (sl.frame_dev) cudaFree(sl.frame_dev);
     if (sl.ctr_host) cudaFreeHost(sl.ctr_host);
     if (sl.fp_host) cudaFreeHost(sl.fp_host);
     for (auto &ev : sl.ev) if (ev) cudaEventDestroy(ev);
+    for (auto &ev : sl.evp) if (ev) cudaEventDestroy(ev);
     if (sl.ev_done) cudaEventDestroy(sl.ev_done);
     if (sl.ev_copied) cudaEventDestroy(sl.ev_copied);
   }
   for (auto &ev : c->ev)
     if (ev) cudaEventDestroy(ev);
+  for (int i = 0; i < 2; ++i) {
+    if (c->ev_fork[i]) cudaEventDestroy(c->ev_fork[i]);
+    if (c->ev_join[i]) cudaEventDestroy(c->ev_join[i]);
+  }
+  if (c->aux_stream) cudaStreamDestroy(c->aux_stream);
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
@@ -390,33 +408,49 @@ extern "C" uint32_t gs_owned_tiles(uint32_t width, uint32_t height, uint32_t ran
 // Everything one frame does on the main stream; all per-frame inputs come from sl.fp (device memory), so the same
 // sequence can be captured once into a CUDA graph and replayed.
 static cudaError_t enqueue_frame(gs_context *c, gs_context::Slot &sl, bool reuse, uint32_t n_tiles, bool external_events) {
-  auto rec = [&](cudaEvent_t ev) {
-    return external_events ? cudaEventRecordWithFlags(ev, c->stream, cudaEventRecordExternal) : cudaEventRecord(ev, c->stream);
+  auto rec = [&](cudaEvent_t ev, cudaStream_t st) {
+    return external_events ? cudaEventRecordWithFlags(ev, st, cudaEventRecordExternal) : cudaEventRecord(ev, st);
   };
+  cudaStream_t m = c->stream, x = c->aux_stream;
   cudaError_t e;
-  if ((e = cudaMemcpyAsync(sl.fp, sl.fp_host, sizeof(FrameParams), cudaMemcpyHostToDevice, c->stream))) return e;
-  if ((e = cudaMemsetAsync(sl.ctr, 0, sizeof(FrameCounters), c->stream))) return e;
-  if ((e = cudaMemsetAsync(c->tile_count, 0, sizeof(uint32_t) * ((size_t)n_tiles + 1), c->stream))) return e;
-  if ((e = rec(sl.ev[0]))) return e;
+  if ((e = cudaMemcpyAsync(sl.fp, sl.fp_host, sizeof(FrameParams), cudaMemcpyHostToDevice, m))) return e;
+  if ((e = cudaMemsetAsync(sl.ctr, 0, sizeof(FrameCounters), m))) return e;
+  if ((e = cudaMemsetAsync(c->tile_count, 0, sizeof(uint32_t) * ((size_t)n_tiles + 1), m))) return e;
+  if ((e = rec(sl.ev[0], m))) return e;
   uint32_t launches = 0;
   if (reuse) {
-    if ((e = cudaMemcpyAsync(sl.ctr, c->sort_hdr, sizeof(SortHeader), cudaMemcpyDeviceToDevice, c->stream))) return e;
+    if ((e = cudaMemcpyAsync(sl.ctr, c->sort_hdr, sizeof(SortHeader), cudaMemcpyDeviceToDevice, m))) return e;
   } else {
     launch_depth_cull(c, sl.fp, sl.ctr);
-    launch_depth_radix(c, sl.ctr);
-    launches += 7;
-    if ((e = cudaMemcpyAsync(c->sort_hdr, sl.ctr, sizeof(SortHeader), cudaMemcpyDeviceToDevice, c->stream))) return e;
+    launches += 1;
   }
-  if ((e = rec(sl.ev[1]))) return e;
-  launch_project(c, sl.fp);
-  if ((e = rec(sl.ev[2]))) return e;
+  // fork 1: the vertex-shader kernel only needs the cull result, so it runs beside the depth radix passes
+  if ((e = cudaEventRecord(c->ev_fork[0], m))) return e;
+  if ((e = cudaStreamWaitEvent(x, c->ev_fork[0], 0))) return e;
+  if ((e = rec(sl.evp[0], x))) return e;
+  launch_project(c, sl.fp, x);
+  if ((e = rec(sl.evp[1], x))) return e;
+  if ((e = cudaEventRecord(c->ev_join[0], x))) return e;
+  if (!reuse) {
+    launch_depth_radix(c, sl.ctr);
+    launches += 6;
+    if ((e = cudaMemcpyAsync(c->sort_hdr, sl.ctr, sizeof(SortHeader), cudaMemcpyDeviceToDevice, m))) return e;
+  }
+  if ((e = rec(sl.ev[1], m))) return e;
+  if ((e = cudaStreamWaitEvent(m, c->ev_join[0], 0))) return e;
+  if ((e = rec(sl.ev[2], m))) return e;
   launch_emit(c, sl.fp, sl.ctr);
+  // fork 2: the tile-range scan only needs the tile counts of k_emit; it runs beside the tile radix passes
+  if ((e = cudaEventRecord(c->ev_fork[1], m))) return e;
+  if ((e = cudaStreamWaitEvent(x, c->ev_fork[1], 0))) return e;
+  launch_tile_scan(c, n_tiles, x);
+  if ((e = cudaEventRecord(c->ev_join[1], x))) return e;
   launch_tile_radix(c, sl.ctr);
-  launch_tile_scan(c, n_tiles);
-  if ((e = rec(sl.ev[3]))) return e;
+  if ((e = cudaStreamWaitEvent(m, c->ev_join[1], 0))) return e;
+  if ((e = rec(sl.ev[3], m))) return e;
   launch_raster(c, sl.fp, n_tiles);
   launches += 11;
-  if ((e = rec(sl.ev[4]))) return e;
+  if ((e = rec(sl.ev[4], m))) return e;
   sl.launches = launches;
   return cudaGetLastError();
 }
@@ -532,7 +566,7 @@ static int wait_slot(gs_context *c, gs_context::Slot &sl, gs_stats *stats) {
   c->stats.width = sl.params.width;
   c->stats.height = sl.params.height;
   cudaEventElapsedTime(&c->stats.ms_sort, sl.ev[0], sl.ev[1]);
-  cudaEventElapsedTime(&c->stats.ms_project, sl.ev[1], sl.ev[2]);
+  cudaEventElapsedTime(&c->stats.ms_project, sl.evp[0], sl.evp[1]);  // on the aux stream, overlapping the sort
   cudaEventElapsedTime(&c->stats.ms_bin, sl.ev[2], sl.ev[3]);
   cudaEventElapsedTime(&c->stats.ms_raster, sl.ev[3], sl.ev[4]);
   cudaEventElapsedTime(&c->stats.ms_total, sl.ev[0], sl.ev[4]);

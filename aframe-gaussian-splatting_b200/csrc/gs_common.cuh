@@ -21,8 +21,8 @@ constexpr int kRadixThreads = 256;
 constexpr int kRadixItems = 16;
 constexpr int kRadixTile = kRadixThreads * kRadixItems;  // 4096 elements per look-back tile
 constexpr int kEmitThreads = 256;
-constexpr int kEmitItems = 4;
-constexpr int kEmitTile = kEmitThreads * kEmitItems;      // 1024 sorted splats per emission tile
+constexpr int kEmitItems = 1;
+constexpr int kEmitTile = kEmitThreads * kEmitItems;      // 256 sorted splats per emission slice (small: near splats own many more instances than far ones)
 constexpr uint32_t kInvalidDigit = 0xFFFFFFFFu;
 constexpr uint32_t kNoRect = 0xFFFFFFFFu;
 constexpr uint16_t kNoTile = 0xFFFFu;
@@ -49,6 +49,7 @@ struct FrameCounters {
   uint32_t n_visible;          // V2
   uint32_t n_inst_kept;        // instances surviving the exact footprint test and the tile-ownership filter
   uint32_t overflow;           // instance buffer too small: frame must be re-run
+  uint32_t count_done;         // k_count CTAs finished (the last one scans the slice totals)
 };
 
 struct RenderConsts {
@@ -108,7 +109,10 @@ struct gs_context {
   uint32_t *table_n = nullptr;   // radix chunk histograms of the depth passes [256][table_n_stride]
   uint32_t table_n_stride = 0;
   uint32_t *totals = nullptr;    // [512]: digit totals of the depth / tile passes
-  uint32_t *tile_total = nullptr;  // instances per 1024-entry emission slice
+  uint32_t *tile_total = nullptr;    // instances per 256-entry slice of the draw order
+  uint32_t *slice_prefix = nullptr;  // exclusive scan of tile_total (+ total at the end)
+  uint2 *ent = nullptr;              // per draw-order entry: {splat index, packed rect or kNoRect}
+  uint32_t *ent_off = nullptr;       // per entry: exclusive instance offset inside its slice
 
   // ---- per-instance scratch (sized to cap_inst) ----
   uint64_t cap_inst = 0;
@@ -137,6 +141,7 @@ struct gs_context {
     void *frame_dev = nullptr;               // used when the caller's buffer is host memory
     size_t frame_bytes = 0;
     cudaEvent_t ev[5]{};                     // stage boundaries (timing)
+    cudaEvent_t evp[2]{};                    // k_project on the aux stream (timing)
     cudaEvent_t ev_done = nullptr, ev_copied = nullptr;
     cudaGraphExec_t graph[2] = {nullptr, nullptr};  // [reuse_sort]
     bool pending = false;
@@ -148,6 +153,8 @@ struct gs_context {
   } slot[2];
   uint64_t next_ticket = 0;
   cudaStream_t copy_stream = nullptr;
+  cudaStream_t aux_stream = nullptr;             // runs k_project / k_tile_scan beside the radix passes
+  cudaEvent_t ev_fork[2]{}, ev_join[2]{};
   bool use_graphs = true;
   // graph cache key: anything baked into the captured launches
   struct GraphKey { uint32_t n = 0, n_tiles = 0; uint64_t cap_inst = 0; const void *p0 = nullptr, *p1 = nullptr, *p2 = nullptr; } gkey;
@@ -165,10 +172,10 @@ namespace gs {
 void launch_depth_cull(gs_context *c, const FrameParams *fp, FrameCounters *ctr);
 void launch_depth_radix(gs_context *c, FrameCounters *ctr);  // 6 launches -> c->order
 void launch_pack(gs_context *c, const uint8_t *rows_dev, uint32_t first, uint32_t n);
-void launch_project(gs_context *c, const FrameParams *fp);
+void launch_project(gs_context *c, const FrameParams *fp, cudaStream_t stream);
 void launch_emit(gs_context *c, const FrameParams *fp, FrameCounters *ctr);  // 2 launches
 void launch_tile_radix(gs_context *c, FrameCounters *ctr);                   // 6 launches
-void launch_tile_scan(gs_context *c, uint32_t n_tiles);
+void launch_tile_scan(gs_context *c, uint32_t n_tiles, cudaStream_t stream);
 void launch_raster(gs_context *c, const FrameParams *fp, uint32_t n_tiles);
 void launch_assemble(gs_context *c, const void *gathered, uint32_t tiles_per_rank, uint32_t world, uint32_t width,
                      uint32_t height, int32_t format, void *out_frame);

@@ -3,9 +3,10 @@
 //
 //   k_project  : fp32 restatement of the vertex shader, op for op (no FMA contraction), producing a
 //                32 B projected record per splat + its packed tile rectangle.
-//   k_count    : instances per 1024-entry slice of the draw order (== reference sortedIndexes) + frame total D.
-//   k_emit     : prefix of those totals + in-slice scan -> writes (tile, splat) instances in draw order, so that a
-//                STABLE sort by tile id alone reproduces the reference's back-to-front order inside every tile.
+//   k_count    : per entry of the draw order (== reference sortedIndexes): instance offset inside its 256-entry slice;
+//                per slice: total; last CTA: prefix over the slices + frame total D.
+//   k_emit     : one CTA per window of 2048 instance positions -> writes (tile, splat) instances in draw order, so
+//                that a STABLE sort by tile id alone reproduces the reference's back-to-front order inside every tile.
 //   k_tile_scan: exclusive scan of the per-tile instance counts -> tile ranges for the raster.
 #include "gs_common.cuh"
 
@@ -142,6 +143,10 @@ __global__ void __launch_bounds__(256) k_project(const float4 *__restrict__ cs, 
   }
 }
 
+
+constexpr int kEmitPerThread = 8;
+constexpr int kEmitWindow = kEmitThreads * kEmitPerThread;  // 2048 instances per CTA iteration
+
 // candidate tiles of a packed rectangle that this rank owns (all of them on one GPU)
 __device__ __forceinline__ uint32_t rect_count(uint32_t r, uint32_t rank, uint32_t world) {
   if (r == kNoRect) return 0u;
@@ -155,176 +160,221 @@ __device__ __forceinline__ uint32_t rect_count(uint32_t r, uint32_t rank, uint32
 }
 
 // ---------------------------------------------------------------------------------------------
-// K3a: instances per emission tile (1024 consecutive draw-order entries) and the frame total D.
+// K3a: per draw-order entry: its splat, rectangle and exclusive instance offset inside its slice of 256
+// entries; per slice: its instance total; the LAST CTA to finish scans the slice totals (-> slice_prefix, D).
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kEmitThreads) k_count(const uint32_t *__restrict__ order,
                                                         const uint32_t *__restrict__ rect,
-                                                        uint32_t *__restrict__ tile_total, FrameCounters *ctr,
+                                                        uint2 *__restrict__ ent, uint32_t *__restrict__ ent_off,
+                                                        uint32_t *__restrict__ slice_total,
+                                                        uint32_t *__restrict__ slice_prefix, FrameCounters *ctr,
                                                         const FrameParams *__restrict__ fp) {
   const uint32_t shard_rank = fp->rc.shard_rank, shard_world = fp->rc.shard_world;
-  __shared__ uint32_t s_sum[kEmitThreads / 32], s_vis[kEmitThreads / 32];
+  __shared__ uint32_t s_warp[kEmitThreads / 32], s_vis[kEmitThreads / 32];
+  __shared__ uint32_t s_last;
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t nv = ctr->n_valid;
-  const uint32_t num_tiles = (nv + kEmitTile - 1) / kEmitTile;
-  for (uint32_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-    const uint32_t j0 = tile * kEmitTile + tid * kEmitItems;
-    uint32_t sum = 0, vis = 0;
-#pragma unroll
-    for (int k = 0; k < kEmitItems; ++k) {
-      const uint32_t j = j0 + k;
-      if (j < nv) {
-        const uint32_t r = __ldg(rect + __ldg(order + j));
-        sum += rect_count(r, shard_rank, shard_world);
-        vis += (r != kNoRect);
-      }
+  const uint32_t num_slices = (nv + kEmitTile - 1) / kEmitTile;
+  for (uint32_t sl = blockIdx.x; sl < num_slices; sl += gridDim.x) {
+    const uint32_t j = sl * kEmitTile + tid;
+    uint32_t idx = 0, r = kNoRect;
+    if (j < nv) {
+      idx = __ldg(order + j);
+      r = __ldg(rect + idx);
     }
-    for (int o = 16; o > 0; o >>= 1) {
-      sum += __shfl_xor_sync(0xffffffffu, sum, o);
-      vis += __shfl_xor_sync(0xffffffffu, vis, o);
-    }
-    if (lane == 0) { s_sum[warp] = sum; s_vis[warp] = vis; }
-    __syncthreads();
-    if (tid == 0) {
-      uint32_t t = 0, v = 0;
-      for (int k = 0; k < kEmitThreads / 32; ++k) { t += s_sum[k]; v += s_vis[k]; }
-      tile_total[tile] = t;
-      if (t) atomicAdd(&ctr->n_inst, (unsigned long long)t);
-      if (v) atomicAdd(&ctr->n_visible, v);
-    }
-    __syncthreads();
-  }
-}
-
-// ---------------------------------------------------------------------------------------------
-// K3b: ordered instance emission.  Instance (entry j, k-th tile of its rectangle) lands at
-// position prefix(j) + k, so the instance array is in draw order whatever the execution order.
-// One thread per instance (balanced expansion); every candidate tile of the bounding rectangle is
-// tested exactly against the r<=2 footprint (closest point of the tile's pixel-centre box in the splat's
-// (px,py) frame) and rejected tiles are written as kNoTile, which the T1 pass drops.
-// ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kEmitThreads, 6) k_emit(const uint32_t *__restrict__ order,
-                                                       const uint32_t *__restrict__ rect,
-                                                       const float4 *__restrict__ proj_rec,
-                                                       const FrameParams *__restrict__ fp, uint64_t cap_inst, const uint32_t *__restrict__ tile_total,
-                                                       uint16_t *__restrict__ inst_tile, uint32_t *__restrict__ inst_idx,
-                                                       uint32_t *__restrict__ tile_count, FrameCounters *ctr) {
-  const RenderConsts &rc = fp->rc;
-  __shared__ uint32_t s_off[kEmitTile];
-  __shared__ uint32_t s_rect[kEmitTile];
-  __shared__ uint32_t s_idx[kEmitTile];
-  __shared__ uint32_t s_warp[kEmitThreads / 32];
-  __shared__ unsigned long long s_red[kEmitThreads / 32];
-  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const uint32_t nv = ctr->n_valid;
-  const uint32_t num_tiles = (nv + kEmitTile - 1) / kEmitTile;
-  if (ctr->n_inst > cap_inst) {  // instance buffer too small: the host regrows it and re-runs the frame
-    if (blockIdx.x == 0 && tid == 0) ctr->overflow = 1u;
-    return;
-  }
-  unsigned long long base = 0;
-  uint32_t summed_upto = 0;  // tile_total[0, summed_upto) is already in `base`
-  for (uint32_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-    // ---- exclusive prefix of the tile totals (block reduction over the not-yet-summed range) ----
-    unsigned long long part = 0;
-    for (uint32_t t = summed_upto + tid; t < tile; t += kEmitThreads) part += tile_total[t];
-    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-    if (lane == 0) s_red[warp] = part;
-    // ---- load the tile's entries ----
-    const uint32_t j0 = tile * kEmitTile + tid * kEmitItems;
-    uint32_t cnt[kEmitItems], sum = 0;
-#pragma unroll
-    for (int k = 0; k < kEmitItems; ++k) {
-      const uint32_t j = j0 + k;
-      uint32_t idx = 0, r = kNoRect;
-      if (j < nv) {
-        idx = __ldg(order + j);
-        r = __ldg(rect + idx);
-      }
-      s_idx[tid * kEmitItems + k] = idx;
-      s_rect[tid * kEmitItems + k] = r;
-      cnt[k] = rect_count(r, rc.shard_rank, rc.shard_world);
-      sum += cnt[k];
-    }
-    uint32_t incl = sum;
+    const uint32_t cnt = rect_count(r, shard_rank, shard_world);
+    uint32_t incl = cnt, vis = (r != kNoRect);
     for (int o = 1; o < 32; o <<= 1) {
       const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
       if (lane >= (uint32_t)o) incl += t;
     }
+    for (int o = 16; o > 0; o >>= 1) vis += __shfl_xor_sync(0xffffffffu, vis, o);
     if (lane == 31) s_warp[warp] = incl;
+    if (lane == 0) s_vis[warp] = vis;
     __syncthreads();
-    uint32_t wbase = 0;
-    for (uint32_t k = 0; k < warp; ++k) wbase += s_warp[k];
-    for (int k = 0; k < kEmitThreads / 32; ++k) base += s_red[k];
-    summed_upto = tile;
-    uint32_t run = wbase + incl - sum;
-#pragma unroll
-    for (int k = 0; k < kEmitItems; ++k) {
-      s_off[tid * kEmitItems + k] = run;
-      run += cnt[k];
+    uint32_t wbase = 0, total = 0, v = 0;
+    for (uint32_t k = 0; k < kEmitThreads / 32; ++k) {
+      if (k < warp) wbase += s_warp[k];
+      total += s_warp[k];
+      v += s_vis[k];
+    }
+    if (j < nv) {
+      ent[j] = make_uint2(idx, cnt ? r : kNoRect);  // entries owning no tile are skipped by the emit walk
+      ent_off[j] = wbase + incl - cnt;
+    }
+    if (tid == 0) {
+      slice_total[sl] = total;
+      if (v) atomicAdd(&ctr->n_visible, v);
     }
     __syncthreads();
-    // ---- expansion: one thread per instance, strided over the slice's instance space (balanced whatever
-    //      the rectangle sizes); the entry of instance e is found by binary search in the scanned offsets ----
-    const uint32_t total = s_off[kEmitTile - 1] + rect_count(s_rect[kEmitTile - 1], rc.shard_rank, rc.shard_world);
-    for (uint32_t e = tid; e < total; e += kEmitThreads) {
-      uint32_t lo = 0, hi = kEmitTile;
-#pragma unroll
-      for (int it = 0; it < 10; ++it) {  // kEmitTile == 1024
+  }
+  // ---- last CTA: exclusive scan of the slice totals ----
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_last = (atomicAdd(&ctr->count_done, 1u) == gridDim.x - 1) ? 1u : 0u;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  unsigned long long carry = 0;
+  for (uint32_t b = 0; b < num_slices; b += kEmitThreads) {
+    const uint32_t i = b + tid;
+    const uint32_t v = (i < num_slices) ? __ldcg(slice_total + i) : 0u;
+    uint32_t incl = v;
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= (uint32_t)o) incl += t;
+    }
+    __syncthreads();
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    uint32_t wbase = 0, total = 0;
+    for (uint32_t k = 0; k < kEmitThreads / 32; ++k) {
+      if (k < warp) wbase += s_warp[k];
+      total += s_warp[k];
+    }
+    // positions are 32-bit: a frame with >= 2^32 candidates overflows the instance buffer long before
+    if (i < num_slices) slice_prefix[i] = (uint32_t)(carry + wbase + incl - v);
+    carry += total;
+  }
+  if (tid == 0) {
+    slice_prefix[num_slices] = (uint32_t)(carry > 0xFFFFFFFFull ? 0xFFFFFFFFull : carry);
+    ctr->n_inst = carry;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K3b: ordered instance emission, balanced by INSTANCES: CTA iteration = one window of 2048 consecutive
+// positions of the instance array (near splats own thousands of tiles, far ones a few: balancing by entries
+// would leave a few CTAs with most of the work).  Thread t generates positions [p0+8t, p0+8t+8): it finds
+// its first entry by two binary searches (slice prefix, then in-slice offsets) and walks on incrementally.
+// Position = prefix(entry) + k, so the array is in draw order whatever the execution order.  Every candidate
+// tile of the bounding rectangle is tested exactly against the r<=2 footprint (closest point of the tile's
+// pixel-centre box in the splat's (px,py) frame); rejected tiles are written as kNoTile and dropped by T1.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kEmitThreads, 6) k_emit(const uint2 *__restrict__ ent,
+                                                          const uint32_t *__restrict__ ent_off,
+                                                          const uint32_t *__restrict__ slice_prefix,
+                                                          const float4 *__restrict__ proj_rec,
+                                                          const FrameParams *__restrict__ fp, uint64_t cap_inst,
+                                                          uint16_t *__restrict__ inst_tile, uint32_t *__restrict__ inst_idx,
+                                                          uint32_t *__restrict__ tile_count, FrameCounters *ctr) {
+  const RenderConsts &rc = fp->rc;
+  __shared__ uint32_t s_wi[kEmitThreads * (kEmitPerThread + 1)];  // stride 9: conflict-free staging
+  __shared__ uint16_t s_wt[kEmitThreads * (kEmitPerThread + 1)];
+  const uint32_t tid = threadIdx.x;
+  const uint32_t nv = ctr->n_valid;
+  const uint32_t num_slices = (nv + kEmitTile - 1) / kEmitTile;
+  const unsigned long long d_all = ctr->n_inst;
+  if (d_all > cap_inst) {  // instance buffer too small: the host regrows it and re-runs the frame
+    if (blockIdx.x == 0 && tid == 0) ctr->overflow = 1u;
+    return;
+  }
+  const uint32_t total = (uint32_t)d_all;
+  const uint32_t num_windows = (total + kEmitWindow - 1) / kEmitWindow;
+  for (uint32_t win = blockIdx.x; win < num_windows; win += gridDim.x) {
+    const uint32_t wb = win * kEmitWindow;
+    const uint32_t e0 = wb + tid * kEmitPerThread;
+    if (e0 < total) {
+      // ---- slice with prefix <= e0 (the last such one: empty slices share their successor's prefix) ----
+      uint32_t lo = 0, hi = num_slices;
+      while (hi - lo > 1) {
         const uint32_t mid = (lo + hi) >> 1;
-        if (s_off[mid] <= e) lo = mid; else hi = mid;
+        if (__ldg(slice_prefix + mid) <= e0) lo = mid; else hi = mid;
       }
-      const uint32_t r = s_rect[lo];
-      const uint32_t idx = s_idx[lo];
-      const uint32_t k = e - s_off[lo];
-      // owned columns of the rectangle: first, first + world, ... (all columns on one GPU)
-      uint32_t tx0 = r & 255u, w = ((r >> 8) & 255u) - tx0 + 1u;
-      const uint32_t ty0 = (r >> 16) & 255u;
-      const uint32_t n_all = w * ((r >> 24) - ty0 + 1u);
-      uint32_t step = 1u;
-      if (rc.shard_world > 1) {
-        owned_span(tx0, (r >> 8) & 255u, rc.shard_rank, rc.shard_world, tx0, w);
-        step = rc.shard_world;
+      const uint32_t in_slice = e0 - __ldg(slice_prefix + lo);
+      // ---- entry inside the slice with offset <= in_slice (the last such one) ----
+      uint32_t a = lo * kEmitTile, b = min(a + (uint32_t)kEmitTile, nv);
+      while (b - a > 1) {
+        const uint32_t mid = (a + b) >> 1;
+        if (__ldg(ent_off + mid) <= in_slice) a = mid; else b = mid;
       }
-      // k / w for k < 65536, w <= 256: float quotient of (k + 0.5) is never within rounding of an integer
-      const uint32_t dy_t = (uint32_t)__fdividef((float)k + 0.5f, (float)w);
-      const uint32_t tx = tx0 + (k - dy_t * w) * step, ty = ty0 + dy_t;
-      bool keep = true;
-      if (n_all > 1) {
-        // footprint geometry: neighbouring instances share the splat, so these gathers mostly hit L1
-        const float4 r0 = __ldg(proj_rec + 2 * (size_t)idx);                       // cx, cy, a1x, a1y
-        const float2 r1 = __ldg((const float2 *)(proj_rec + 2 * (size_t)idx + 1));  // a2x, a2y
-        // pixel-centre box of the tile, relative to the splat centre
-        const float xa = (float)(tx * kTile) + 0.5f - r0.x, xb = xa + 15.0f;
-        const float ya = (float)(ty * kTile) + 0.5f - r0.y, yb = ya + 15.0f;
-        const bool in_x = (xa <= 0.0f) && (xb >= 0.0f), in_y = (ya <= 0.0f) && (yb >= 0.0f);
-        if (!(in_x && in_y)) {
-          float qmin = 3.0e38f;
-          if (!in_x) {  // nearest vertical edge, minimise over y on it
-            const float dx = (xa > 0.0f) ? xa : xb;
-            const float px0 = dx * r1.x, py0 = dx * r0.z;
-            float t = -__fdividef(px0 * r1.y + py0 * r0.w, r1.y * r1.y + r0.w * r0.w);
-            t = fminf(fmaxf(t, ya), yb);
-            const float px = px0 + t * r1.y, py = py0 + t * r0.w;
-            qmin = px * px + py * py;
-          }
-          if (!in_y) {  // nearest horizontal edge, minimise over x on it
-            const float dy = (ya > 0.0f) ? ya : yb;
-            const float px0 = dy * r1.y, py0 = dy * r0.w;
-            float t = -__fdividef(px0 * r1.x + py0 * r0.z, r1.x * r1.x + r0.z * r0.z);
-            t = fminf(fmaxf(t, xa), xb);
-            const float px = px0 + t * r1.x, py = py0 + t * r0.z;
-            qmin = fminf(qmin, px * px + py * py);
-          }
-          keep = !(qmin > 4.02f);  // r^2 <= 4 with slack for fp32 rounding of the closest-point search
+      uint32_t j = a;                                  // current entry
+      uint32_t k = in_slice - __ldg(ent_off + a);      // position inside it
+      uint32_t idx = 0, txf = 0, w = 1, step = 1, tx = 0, ty = 0, n_all = 0, n_own = 0;
+      float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f);
+      float2 r1 = make_float2(0.f, 0.f);
+      float cross = 0.f, inv_yy = 0.f, inv_xx = 0.f;
+      auto load_entry = [&](uint32_t jj, uint32_t kk) {
+        const uint2 en = __ldg(ent + jj);
+        const uint32_t r = en.y;
+        n_own = 0;
+        if (r == kNoRect) return;
+        idx = en.x;
+        uint32_t tx0 = r & 255u;
+        const uint32_t ty0 = (r >> 16) & 255u, h = (r >> 24) - ty0 + 1u;
+        w = ((r >> 8) & 255u) - tx0 + 1u;
+        n_all = w * h;
+        step = 1u;
+        if (rc.shard_world > 1) {  // owned columns of the rectangle: first, first + world, ...
+          owned_span(tx0, (r >> 8) & 255u, rc.shard_rank, rc.shard_world, tx0, w);
+          step = rc.shard_world;
         }
+        n_own = w * h;
+        if (n_own == 0) return;
+        txf = tx0;
+        // kk / w for kk < 65536, w <= 256: the float quotient of (kk + 0.5) is never within rounding of an integer
+        const uint32_t row = (uint32_t)__fdividef((float)kk + 0.5f, (float)w);
+        tx = tx0 + (kk - row * w) * step;
+        ty = ty0 + row;
+        if (n_all > 1) {  // footprint geometry for the exact tile test
+          r0 = __ldg(proj_rec + 2 * (size_t)idx);                        // cx, cy, a1x, a1y
+          r1 = __ldg((const float2 *)(proj_rec + 2 * (size_t)idx + 1));  // a2x, a2y
+          // q(d) = |(a2.d, a1.d)|^2 = M00 dx^2 + 2 M01 dx dy + M11 dy^2: edge minimisers need M01/M11 and M01/M00
+          cross = r1.x * r1.y + r0.z * r0.w;
+          inv_yy = __fdividef(1.0f, r1.y * r1.y + r0.w * r0.w);
+          inv_xx = __fdividef(1.0f, r1.x * r1.x + r0.z * r0.z);
+        }
+      };
+      load_entry(j, k);
+#pragma unroll 1
+      for (uint32_t q = 0; q < (uint32_t)kEmitPerThread && e0 + q < total; ++q) {
+        while (k >= n_own) {  // next entry that owns tiles
+          ++j;
+          load_entry(j, 0u);
+          k = 0;
+        }
+        bool keep = true;
+        if (n_all > 1) {
+          // pixel-centre box of the tile, relative to the splat centre
+          const float xa = (float)(tx * kTile) + 0.5f - r0.x, xb = xa + 15.0f;
+          const float ya = (float)(ty * kTile) + 0.5f - r0.y, yb = ya + 15.0f;
+          const bool in_x = (xa <= 0.0f) && (xb >= 0.0f), in_y = (ya <= 0.0f) && (yb >= 0.0f);
+          if (!(in_x && in_y)) {
+            float qmin = 3.0e38f;
+            if (!in_x) {  // nearest vertical edge, minimise over y on it; (px,py) evaluated at the found point
+              const float dx = (xa > 0.0f) ? xa : xb;
+              const float t = fminf(fmaxf(-dx * cross * inv_yy, ya), yb);
+              const float px = dx * r1.x + t * r1.y, py = dx * r0.z + t * r0.w;
+              qmin = px * px + py * py;
+            }
+            if (!in_y) {  // nearest horizontal edge, minimise over x on it
+              const float dy = (ya > 0.0f) ? ya : yb;
+              const float t = fminf(fmaxf(-dy * cross * inv_xx, xa), xb);
+              const float px = t * r1.x + dy * r1.y, py = t * r0.z + dy * r0.w;
+              qmin = fminf(qmin, px * px + py * py);
+            }
+            keep = !(qmin > 4.02f);  // r^2 <= 4 with slack for fp32 rounding of the closest-point search
+          }
+        }
+        uint32_t t = kNoTile;
+        if (keep) {
+          t = ty * rc.tiles_x + tx;
+          atomicAdd(tile_count + t, 1u);
+        }
+        s_wt[tid * (kEmitPerThread + 1) + q] = (uint16_t)t;
+        s_wi[tid * (kEmitPerThread + 1) + q] = idx;
+        // advance inside the rectangle (row-major over the owned columns)
+        ++k;
+        tx += step;
+        if (tx >= txf + w * step) { tx = txf; ++ty; }
       }
-      uint32_t t = kNoTile;
-      if (keep) {
-        t = ty * rc.tiles_x + tx;
-        atomicAdd(tile_count + t, 1u);
-      }
-      inst_tile[base + e] = (uint16_t)t;
-      inst_idx[base + e] = idx;
+    }
+    __syncthreads();
+    const uint32_t wn = min((uint32_t)kEmitWindow, total - wb);
+    for (uint32_t i = tid; i < wn; i += kEmitThreads) {
+      const uint32_t si = (i / kEmitPerThread) * (kEmitPerThread + 1) + (i % kEmitPerThread);
+      inst_tile[(size_t)wb + i] = s_wt[si];
+      inst_idx[(size_t)wb + i] = s_wi[si];
     }
     __syncthreads();
   }
@@ -359,12 +409,12 @@ __global__ void __launch_bounds__(1024) k_tile_scan(const uint32_t *__restrict__
   if (tid == 0) tile_start[n_tiles] = s_carry;
 }
 
-void launch_project(gs_context *c, const FrameParams *fp) {
+void launch_project(gs_context *c, const FrameParams *fp, cudaStream_t stream) {
   uint64_t blocks = ((uint64_t)c->n + 255) / 256;
   const uint64_t cap = (uint64_t)c->sm_count * 16;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
-  k_project<<<(int)blocks, 256, 0, c->stream>>>(c->center_scale, c->cov_color, c->depth, c->n, fp, c->proj_rec, c->rect);
+  k_project<<<(int)blocks, 256, 0, stream>>>(c->center_scale, c->cov_color, c->depth, c->n, fp, c->proj_rec, c->rect);
 }
 
 void launch_emit(gs_context *c, const FrameParams *fp, FrameCounters *ctr) {
@@ -372,13 +422,17 @@ void launch_emit(gs_context *c, const FrameParams *fp, FrameCounters *ctr) {
   const uint64_t cap = (uint64_t)c->sm_count * 8;
   if (tiles > cap) tiles = cap;
   if (tiles < 1) tiles = 1;
-  k_count<<<(int)tiles, kEmitThreads, 0, c->stream>>>(c->order, c->rect, c->tile_total, ctr, fp);
-  k_emit<<<(int)tiles, kEmitThreads, 0, c->stream>>>(c->order, c->rect, c->proj_rec, fp, c->cap_inst, c->tile_total,
-                                                     c->inst_tile, c->inst_idx, c->tile_count, ctr);
+  k_count<<<(int)tiles, kEmitThreads, 0, c->stream>>>(c->order, c->rect, c->ent, c->ent_off, c->tile_total,
+                                                      c->slice_prefix, ctr, fp);
+  uint64_t wins = (c->cap_inst + kEmitWindow - 1) / kEmitWindow;
+  if (wins > (uint64_t)c->sm_count * 6) wins = (uint64_t)c->sm_count * 6;
+  if (wins < 1) wins = 1;
+  k_emit<<<(int)wins, kEmitThreads, 0, c->stream>>>(c->ent, c->ent_off, c->slice_prefix, c->proj_rec, fp, c->cap_inst,
+                                                    c->inst_tile, c->inst_idx, c->tile_count, ctr);
 }
 
-void launch_tile_scan(gs_context *c, uint32_t n_tiles) {
-  k_tile_scan<<<1, 1024, 0, c->stream>>>(c->tile_count, n_tiles, c->tile_start);
+void launch_tile_scan(gs_context *c, uint32_t n_tiles, cudaStream_t stream) {
+  k_tile_scan<<<1, 1024, 0, stream>>>(c->tile_count, n_tiles, c->tile_start);
 }
 
 }  // namespace gs

@@ -9,15 +9,15 @@
 //   back-to-front (reference):  C <- c*a + C*(1-a),  A <- a + A*(1-a)      (index.js:177-178)
 //   front-to-back (here):       C  = sum_i c_i a_i T_i + bg*T_end,  A = 1 - T_end + bg.a*T_end,
 //                               T_i = prod_{j nearer than i} (1 - a_j)      
-// The two are algebraically identical; a tile stops early once every pixel has T < 1e-4, which bounds the
-// dropped contribution by 1e-4 per channel (the parity tolerance is 1e-3).
+// The two are algebraically identical; a tile stops early once every pixel has T < 3e-4, which bounds the
+// dropped contribution by 3e-4 per channel (the parity tolerance is 1e-3).
 #include "gs_common.cuh"
 
 namespace gs {
 
 constexpr int kChunk = 128;   // records per TMA bulk copy (4 KB)
 constexpr int kStages = 4;    // ring depth
-constexpr float kTStop = 1e-4f;
+constexpr float kTStop = 3e-4f;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -70,7 +70,8 @@ __global__ void __launch_bounds__(256) k_raster(const float4 *__restrict__ inst_
   if (rc.shard_world > 1 && (tx % rc.shard_world) != rc.shard_rank) return;
 
   const uint32_t tid = threadIdx.x;
-  const uint32_t lx = tid & 15u, ly = tid >> 4;
+  // a warp owns a compact 8x4 pixel block (fewer splats straddle it than a 16x2 strip): tid = [ty2 tx1 | y2 x3]
+  const uint32_t lx = ((tid >> 5) & 1u) * 8u + (tid & 7u), ly = (tid >> 6) * 4u + ((tid >> 3) & 3u);
   const uint32_t x = tx * kTile + lx, y = ty * kTile + ly;
   const bool inside = (x < rc.width) && (y < rc.height);
   const float fx = (float)x + 0.5f, fy = (float)y + 0.5f;  // pixel centre, GL window coordinates
@@ -152,7 +153,7 @@ __global__ void __launch_bounds__(256) k_raster(const float4 *__restrict__ inst_
   if (rc.out_tiled) {
     const uint32_t slot =
         (rc.shard_world > 1) ? owned_slot(tx, ty, rc.tiles_x, rc.shard_rank, rc.shard_world) : tile;
-    pix = (size_t)slot * 256 + tid;
+    pix = (size_t)slot * 256 + ly * 16 + lx;
     write = true;
   } else {
     pix = (size_t)y * rc.width + x;

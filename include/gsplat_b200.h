@@ -71,7 +71,8 @@ typedef struct gs_stats {
   uint32_t width, height;  /*     frame size (P = width*height)                              */
   double min_depth, max_depth; /* fp64 depth range of the sorted set (index.js:552-553)      */
   float ms_sort;           /* depth/cull + histogram + two radix passes                      */
-  float ms_project;        /* per-splat projection + tile rect                               */
+  float ms_project;        /* per-splat projection + tile rect (runs beside the sort's radix
+                              passes on a second stream: overlaps ms_sort)                    */
   float ms_bin;            /* instance emission + two tile-radix passes                      */
   float ms_raster;         /* tile raster + composite                                        */
   float ms_total;          /* whole frame on the device (events on the context's stream)     */
