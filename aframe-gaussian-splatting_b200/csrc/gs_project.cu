@@ -245,13 +245,36 @@ __global__ void __launch_bounds__(kEmitThreads) k_count(const uint32_t *__restri
 // ---------------------------------------------------------------------------------------------
 // K3b: ordered instance emission, balanced by INSTANCES: CTA iteration = one window of 2048 consecutive
 // positions of the instance array (near splats own thousands of tiles, far ones a few: balancing by entries
-// would leave a few CTAs with most of the work).  Thread t generates positions [p0+8t, p0+8t+8): it finds
-// its first entry by two binary searches (slice prefix, then in-slice offsets) and walks on incrementally.
-// Position = prefix(entry) + k, so the array is in draw order whatever the execution order.  Every candidate
-// tile of the bounding rectangle is tested exactly against the r<=2 footprint (closest point of the tile's
-// pixel-centre box in the splat's (px,py) frame); rejected tiles are written as kNoTile and dropped by T1.
+// would leave a few CTAs with most of the work).
+//   1. two warps locate the window's first / last draw-order entry with 32-ary searches (5 dependent loads);
+//   2. the entries of the window (and the footprint geometry of their splats) are staged in shared memory,
+//      coalesced, at most kEmitEnt at a time;
+//   3. thread t generates positions [8t, 8t+8) of the window: one binary search in shared memory, then an
+//      incremental walk over tiles / entries; every candidate tile of the bounding rectangle is tested exactly
+//      against the r<=2 footprint (closest point of the tile's pixel-centre box in the splat's (px,py) frame),
+//      rejected tiles become kNoTile and are dropped by the T1 pass;
+//   4. the window is written out coalesced.
+// Position = prefix(entry) + k, so the array is in draw order whatever the execution order.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kEmitThreads, 6) k_emit(const uint2 *__restrict__ ent,
+constexpr int kEmitEnt = 896;  // staged entries per pass (static shared memory stays under 48 KB)
+
+// largest i in [lo, hi) with key(i) <= p, keys non-decreasing, key(lo) <= p; all 32 lanes of a warp cooperate
+template <class F>
+__device__ __forceinline__ uint32_t warp_search_le(uint32_t lo, uint32_t hi, uint32_t p, F key) {
+  const uint32_t lane = threadIdx.x & 31;
+  while (hi - lo > 1) {
+    const uint32_t step = (hi - lo + 31) / 32;
+    const uint32_t i = lo + lane * step;
+    const bool ok = (i < hi) && (key(i) <= p);
+    const uint32_t c = __popc(__ballot_sync(0xffffffffu, ok));  // lanes 0..c-1 are ok (c >= 1)
+    const uint32_t nlo = lo + (c - 1) * step;
+    hi = min(hi, nlo + step);
+    lo = nlo;
+  }
+  return lo;
+}
+
+__global__ void __launch_bounds__(kEmitThreads, 4) k_emit(const uint2 *__restrict__ ent,
                                                           const uint32_t *__restrict__ ent_off,
                                                           const uint32_t *__restrict__ slice_prefix,
                                                           const float4 *__restrict__ proj_rec,
@@ -261,7 +284,12 @@ __global__ void __launch_bounds__(kEmitThreads, 6) k_emit(const uint2 *__restric
   const RenderConsts &rc = fp->rc;
   __shared__ uint32_t s_wi[kEmitThreads * (kEmitPerThread + 1)];  // stride 9: conflict-free staging
   __shared__ uint16_t s_wt[kEmitThreads * (kEmitPerThread + 1)];
-  const uint32_t tid = threadIdx.x;
+  __shared__ uint2 s_ent[kEmitEnt];         // {splat index, rect}
+  __shared__ uint32_t s_goff[kEmitEnt + 1];  // global instance offset of each staged entry
+  __shared__ float4 s_g0[kEmitEnt];         // cx, cy, a1x, a1y
+  __shared__ float2 s_g1[kEmitEnt];         // a2x, a2y
+  __shared__ uint32_t s_jfl[2];
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t nv = ctr->n_valid;
   const uint32_t num_slices = (nv + kEmitTile - 1) / kEmitTile;
   const unsigned long long d_all = ctr->n_inst;
@@ -271,106 +299,145 @@ __global__ void __launch_bounds__(kEmitThreads, 6) k_emit(const uint2 *__restric
   }
   const uint32_t total = (uint32_t)d_all;
   const uint32_t num_windows = (total + kEmitWindow - 1) / kEmitWindow;
+  auto goff = [&](uint32_t j) -> uint32_t {  // global instance offset of entry j (j == nv: the total)
+    return j < nv ? __ldg(slice_prefix + (j >> 8)) + __ldg(ent_off + j) : total;
+  };
+  static_assert(kEmitTile == 256, "entry -> slice is j >> 8");
+
   for (uint32_t win = blockIdx.x; win < num_windows; win += gridDim.x) {
-    const uint32_t wb = win * kEmitWindow;
-    const uint32_t e0 = wb + tid * kEmitPerThread;
-    if (e0 < total) {
-      // ---- slice with prefix <= e0 (the last such one: empty slices share their successor's prefix) ----
-      uint32_t lo = 0, hi = num_slices;
-      while (hi - lo > 1) {
-        const uint32_t mid = (lo + hi) >> 1;
-        if (__ldg(slice_prefix + mid) <= e0) lo = mid; else hi = mid;
-      }
-      const uint32_t in_slice = e0 - __ldg(slice_prefix + lo);
-      // ---- entry inside the slice with offset <= in_slice (the last such one) ----
-      uint32_t a = lo * kEmitTile, b = min(a + (uint32_t)kEmitTile, nv);
-      while (b - a > 1) {
-        const uint32_t mid = (a + b) >> 1;
-        if (__ldg(ent_off + mid) <= in_slice) a = mid; else b = mid;
-      }
-      uint32_t j = a;                                  // current entry
-      uint32_t k = in_slice - __ldg(ent_off + a);      // position inside it
-      uint32_t idx = 0, txf = 0, w = 1, step = 1, tx = 0, ty = 0, n_all = 0, n_own = 0;
-      float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f);
-      float2 r1 = make_float2(0.f, 0.f);
-      float cross = 0.f, inv_yy = 0.f, inv_xx = 0.f;
-      auto load_entry = [&](uint32_t jj, uint32_t kk) {
-        const uint2 en = __ldg(ent + jj);
-        const uint32_t r = en.y;
-        n_own = 0;
-        if (r == kNoRect) return;
-        idx = en.x;
-        uint32_t tx0 = r & 255u;
-        const uint32_t ty0 = (r >> 16) & 255u, h = (r >> 24) - ty0 + 1u;
-        w = ((r >> 8) & 255u) - tx0 + 1u;
-        n_all = w * h;
-        step = 1u;
-        if (rc.shard_world > 1) {  // owned columns of the rectangle: first, first + world, ...
-          owned_span(tx0, (r >> 8) & 255u, rc.shard_rank, rc.shard_world, tx0, w);
-          step = rc.shard_world;
-        }
-        n_own = w * h;
-        if (n_own == 0) return;
-        txf = tx0;
-        // kk / w for kk < 65536, w <= 256: the float quotient of (kk + 0.5) is never within rounding of an integer
-        const uint32_t row = (uint32_t)__fdividef((float)kk + 0.5f, (float)w);
-        tx = tx0 + (kk - row * w) * step;
-        ty = ty0 + row;
-        if (n_all > 1) {  // footprint geometry for the exact tile test
-          r0 = __ldg(proj_rec + 2 * (size_t)idx);                        // cx, cy, a1x, a1y
-          r1 = __ldg((const float2 *)(proj_rec + 2 * (size_t)idx + 1));  // a2x, a2y
-          // q(d) = |(a2.d, a1.d)|^2 = M00 dx^2 + 2 M01 dx dy + M11 dy^2: edge minimisers need M01/M11 and M01/M00
-          cross = r1.x * r1.y + r0.z * r0.w;
-          inv_yy = __fdividef(1.0f, r1.y * r1.y + r0.w * r0.w);
-          inv_xx = __fdividef(1.0f, r1.x * r1.x + r0.z * r0.z);
-        }
-      };
-      load_entry(j, k);
-#pragma unroll 1
-      for (uint32_t q = 0; q < (uint32_t)kEmitPerThread && e0 + q < total; ++q) {
-        while (k >= n_own) {  // next entry that owns tiles
-          ++j;
-          load_entry(j, 0u);
-          k = 0;
-        }
-        bool keep = true;
-        if (n_all > 1) {
-          // pixel-centre box of the tile, relative to the splat centre
-          const float xa = (float)(tx * kTile) + 0.5f - r0.x, xb = xa + 15.0f;
-          const float ya = (float)(ty * kTile) + 0.5f - r0.y, yb = ya + 15.0f;
-          const bool in_x = (xa <= 0.0f) && (xb >= 0.0f), in_y = (ya <= 0.0f) && (yb >= 0.0f);
-          if (!(in_x && in_y)) {
-            float qmin = 3.0e38f;
-            if (!in_x) {  // nearest vertical edge, minimise over y on it; (px,py) evaluated at the found point
-              const float dx = (xa > 0.0f) ? xa : xb;
-              const float t = fminf(fmaxf(-dx * cross * inv_yy, ya), yb);
-              const float px = dx * r1.x + t * r1.y, py = dx * r0.z + t * r0.w;
-              qmin = px * px + py * py;
-            }
-            if (!in_y) {  // nearest horizontal edge, minimise over x on it
-              const float dy = (ya > 0.0f) ? ya : yb;
-              const float t = fminf(fmaxf(-dy * cross * inv_xx, xa), xb);
-              const float px = t * r1.x + dy * r1.y, py = t * r0.z + dy * r0.w;
-              qmin = fminf(qmin, px * px + py * py);
-            }
-            keep = !(qmin > 4.02f);  // r^2 <= 4 with slack for fp32 rounding of the closest-point search
-          }
-        }
-        uint32_t t = kNoTile;
-        if (keep) {
-          t = ty * rc.tiles_x + tx;
-          atomicAdd(tile_count + t, 1u);
-        }
-        s_wt[tid * (kEmitPerThread + 1) + q] = (uint16_t)t;
-        s_wi[tid * (kEmitPerThread + 1) + q] = idx;
-        // advance inside the rectangle (row-major over the owned columns)
-        ++k;
-        tx += step;
-        if (tx >= txf + w * step) { tx = txf; ++ty; }
-      }
+    const uint32_t wb = win * kEmitWindow, we = min(wb + (uint32_t)kEmitWindow, total);
+    // ---- 1. first / last entry of the window ----
+    if (warp < 2) {
+      const uint32_t p = warp == 0 ? wb : we - 1;
+      const uint32_t sl = warp_search_le(0u, num_slices, p, [&](uint32_t i) { return __ldg(slice_prefix + i); });
+      const uint32_t rel = p - __ldg(slice_prefix + sl);
+      const uint32_t a = sl * kEmitTile, b = min(a + (uint32_t)kEmitTile, nv);
+      const uint32_t j = warp_search_le(a, b, rel, [&](uint32_t i) { return __ldg(ent_off + i); });
+      if (lane == 0) s_jfl[warp] = j;
     }
     __syncthreads();
-    const uint32_t wn = min((uint32_t)kEmitWindow, total - wb);
+    const uint32_t j_last = s_jfl[1];
+    uint32_t j0 = s_jfl[0], pos = wb;
+    while (pos < we) {
+      // ---- 2. stage entries [j0, jE) ----
+      const uint32_t jE = min(j0 + (uint32_t)kEmitEnt, j_last + 1);
+      const uint32_t nE = jE - j0;
+      for (uint32_t i = tid; i <= nE; i += kEmitThreads) {
+        s_goff[i] = goff(j0 + i);
+        if (i < nE) {
+          const uint2 en = __ldg(ent + j0 + i);
+          s_ent[i] = en;
+          const uint32_t r = en.y;
+          if (r != kNoRect) {
+            const uint32_t wfull = ((r >> 8) & 255u) - (r & 255u) + 1u, hfull = (r >> 24) - ((r >> 16) & 255u) + 1u;
+            if (wfull * hfull > 1u) {  // footprint geometry for the exact tile test
+              s_g0[i] = __ldg(proj_rec + 2 * (size_t)en.x);
+              s_g1[i] = __ldg((const float2 *)(proj_rec + 2 * (size_t)en.x + 1));
+            }
+          }
+        }
+      }
+      __syncthreads();
+      const uint32_t pe = min(we, s_goff[nE]);  // positions [pos, pe) belong to the staged entries
+      // ---- 3. generate ----
+      const uint32_t t0 = max(pos, wb + tid * kEmitPerThread), t1 = min(pe, wb + (tid + 1) * kEmitPerThread);
+      if (t0 < t1) {
+        uint32_t lo = 0, hi = nE;
+        while (hi - lo > 1) {
+          const uint32_t mid = (lo + hi) >> 1;
+          if (s_goff[mid] <= t0) lo = mid; else hi = mid;
+        }
+        uint32_t e = lo;                  // staged entry
+        uint32_t k = t0 - s_goff[lo];     // position inside it
+        uint32_t idx = 0, txf = 0, w = 1, step = 1, tx = 0, ty = 0, n_all = 0, n_own = 0;
+        float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f);
+        float2 r1 = make_float2(0.f, 0.f);
+        float cross = 0.f, inv_yy = 0.f, inv_xx = 0.f;
+        auto load_entry = [&](uint32_t ee, uint32_t kk) {
+          const uint2 en = s_ent[ee];
+          const uint32_t r = en.y;
+          n_own = 0;
+          if (r == kNoRect) return;
+          idx = en.x;
+          uint32_t tx0 = r & 255u;
+          const uint32_t ty0 = (r >> 16) & 255u, h = (r >> 24) - ty0 + 1u;
+          w = ((r >> 8) & 255u) - tx0 + 1u;
+          n_all = w * h;
+          step = 1u;
+          if (rc.shard_world > 1) {  // owned columns of the rectangle: first, first + world, ...
+            owned_span(tx0, (r >> 8) & 255u, rc.shard_rank, rc.shard_world, tx0, w);
+            step = rc.shard_world;
+          }
+          n_own = w * h;
+          if (n_own == 0) return;
+          txf = tx0;
+          // kk / w for kk < 65536, w <= 256: the float quotient of (kk + 0.5) is never within rounding of an integer
+          const uint32_t row = (uint32_t)__fdividef((float)kk + 0.5f, (float)w);
+          tx = tx0 + (kk - row * w) * step;
+          ty = ty0 + row;
+          if (n_all > 1) {
+            r0 = s_g0[ee];
+            r1 = s_g1[ee];
+            // q(d) = |(a2.d, a1.d)|^2 = M00 dx^2 + 2 M01 dx dy + M11 dy^2: edge minimisers need M01/M11, M01/M00
+            cross = r1.x * r1.y + r0.z * r0.w;
+            inv_yy = __fdividef(1.0f, r1.y * r1.y + r0.w * r0.w);
+            inv_xx = __fdividef(1.0f, r1.x * r1.x + r0.z * r0.z);
+          }
+        };
+        load_entry(e, k);
+#pragma unroll 1
+        for (uint32_t p = t0; p < t1; ++p) {
+          while (k >= n_own) {  // next staged entry that owns tiles
+            ++e;
+            load_entry(e, 0u);
+            k = 0;
+          }
+          bool keep = true;
+          if (n_all > 1) {
+            // pixel-centre box of the tile, relative to the splat centre
+            const float xa = (float)(tx * kTile) + 0.5f - r0.x, xb = xa + 15.0f;
+            const float ya = (float)(ty * kTile) + 0.5f - r0.y, yb = ya + 15.0f;
+            const bool in_x = (xa <= 0.0f) && (xb >= 0.0f), in_y = (ya <= 0.0f) && (yb >= 0.0f);
+            if (!(in_x && in_y)) {
+              float qmin = 3.0e38f;
+              if (!in_x) {  // nearest vertical edge, minimise over y on it; (px,py) evaluated at the found point
+                const float dx = (xa > 0.0f) ? xa : xb;
+                const float t = fminf(fmaxf(-dx * cross * inv_yy, ya), yb);
+                const float px = dx * r1.x + t * r1.y, py = dx * r0.z + t * r0.w;
+                qmin = px * px + py * py;
+              }
+              if (!in_y) {  // nearest horizontal edge, minimise over x on it
+                const float dy = (ya > 0.0f) ? ya : yb;
+                const float t = fminf(fmaxf(-dy * cross * inv_xx, xa), xb);
+                const float px = t * r1.x + dy * r1.y, py = t * r0.z + dy * r0.w;
+                qmin = fminf(qmin, px * px + py * py);
+              }
+              keep = !(qmin > 4.02f);  // r^2 <= 4 with slack for fp32 rounding of the closest-point search
+            }
+          }
+          uint32_t t = kNoTile;
+          if (keep) {
+            t = ty * rc.tiles_x + tx;
+#ifndef GS_EXP_NO_ATOMIC
+            atomicAdd(tile_count + t, 1u);
+#endif
+          }
+          const uint32_t q = p - wb;  // window-relative position
+          const uint32_t si = (q / kEmitPerThread) * (kEmitPerThread + 1) + (q % kEmitPerThread);
+          s_wt[si] = (uint16_t)t;
+          s_wi[si] = idx;
+          // advance inside the rectangle (row-major over the owned columns)
+          ++k;
+          tx += step;
+          if (tx >= txf + w * step) { tx = txf; ++ty; }
+        }
+      }
+      __syncthreads();
+      pos = pe;
+      j0 = jE;
+    }
+    // ---- 4. write the window out ----
+    const uint32_t wn = we - wb;
     for (uint32_t i = tid; i < wn; i += kEmitThreads) {
       const uint32_t si = (i / kEmitPerThread) * (kEmitPerThread + 1) + (i % kEmitPerThread);
       inst_tile[(size_t)wb + i] = s_wt[si];
@@ -425,7 +492,7 @@ void launch_emit(gs_context *c, const FrameParams *fp, FrameCounters *ctr) {
   k_count<<<(int)tiles, kEmitThreads, 0, c->stream>>>(c->order, c->rect, c->ent, c->ent_off, c->tile_total,
                                                       c->slice_prefix, ctr, fp);
   uint64_t wins = (c->cap_inst + kEmitWindow - 1) / kEmitWindow;
-  if (wins > (uint64_t)c->sm_count * 6) wins = (uint64_t)c->sm_count * 6;
+  if (wins > (uint64_t)c->sm_count * 4) wins = (uint64_t)c->sm_count * 4;
   if (wins < 1) wins = 1;
   k_emit<<<(int)wins, kEmitThreads, 0, c->stream>>>(c->ent, c->ent_off, c->slice_prefix, c->proj_rec, fp, c->cap_inst,
                                                     c->inst_tile, c->inst_idx, c->tile_count, ctr);
