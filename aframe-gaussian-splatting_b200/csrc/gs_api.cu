@@ -101,9 +101,10 @@ static int ensure_scratch(gs_context *c) {
 }
 
 static int ensure_instances(gs_context *c, uint64_t need) {
-  if (need <= c->cap_inst && c->inst_rec) return GS_OK;
+  if (need <= c->cap_inst && c->inst_rec[0]) return GS_OK;
   if (need >= (1ull << 30)) return fail(c, GS_ERR_CAPACITY, "more than 2^30 tile instances in one frame");
-  dev_free(c->inst_tile); dev_free(c->inst_idx); dev_free(c->inst_dig_b); dev_free(c->inst_idx_b); dev_free(c->inst_rec);
+  dev_free(c->inst_tile); dev_free(c->inst_idx); dev_free(c->inst_dig_b); dev_free(c->inst_idx_b);
+  dev_free(c->inst_rec[0]); dev_free(c->inst_rec[1]);
   dev_free(c->table_d);
   c->table_d_stride = (uint32_t)((need + kRadixTile - 1) / kRadixTile + 1);
   GS_CUDA(c, dev_alloc(&c->table_d, (size_t)256 * c->table_d_stride));
@@ -111,16 +112,18 @@ static int ensure_instances(gs_context *c, uint64_t need) {
   GS_CUDA(c, dev_alloc(&c->inst_idx, need));
   GS_CUDA(c, dev_alloc(&c->inst_dig_b, need));
   GS_CUDA(c, dev_alloc(&c->inst_idx_b, need));
-  GS_CUDA(c, dev_alloc(&c->inst_rec, 2 * need));
+  GS_CUDA(c, dev_alloc(&c->inst_rec[0], 2 * need));
+  GS_CUDA(c, dev_alloc(&c->inst_rec[1], 2 * need));
   c->cap_inst = need;
   return GS_OK;
 }
 
 static int ensure_tiles(gs_context *c, uint32_t n_tiles) {
   if (n_tiles <= c->tiles_cap && c->tile_count) return GS_OK;
-  dev_free(c->tile_count); dev_free(c->tile_start);
+  dev_free(c->tile_count); dev_free(c->tile_start[0]); dev_free(c->tile_start[1]);
   GS_CUDA(c, dev_alloc(&c->tile_count, (size_t)n_tiles + 1));
-  GS_CUDA(c, dev_alloc(&c->tile_start, (size_t)n_tiles + 2));
+  GS_CUDA(c, dev_alloc(&c->tile_start[0], (size_t)n_tiles + 2));
+  GS_CUDA(c, dev_alloc(&c->tile_start[1], (size_t)n_tiles + 2));
   c->tiles_cap = n_tiles;
   return GS_OK;
 }
@@ -135,9 +138,11 @@ static int ensure_frame(gs_context *c, gs_context::Slot &sl, size_t bytes) {
 }
 
 static void drop_graphs(gs_context *c) {
-  for (auto &sl : c->slot)
+  for (auto &sl : c->slot) {
     for (auto &g : sl.graph)
       if (g) { cudaGraphExecDestroy(g); g = nullptr; }
+    if (sl.graph_r) { cudaGraphExecDestroy(sl.graph_r); sl.graph_r = nullptr; }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -179,9 +184,16 @@ extern "C" int gs_create(int device_ordinal, gs_context **out_ctx) {
     return GS_ERR_CUDA;
   };
   if ((e = cudaSetDevice(device_ordinal)) != cudaSuccess) return bail("cudaSetDevice", e);
-  if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+  // sort + binning kernels are short and latency-bound, the raster is one long issue-bound kernel: giving the
+  // main / aux streams priority lets their CTAs slot in as raster CTAs retire, so frame k+1 is binned UNDER frame k's raster
+  int prio_least = 0, prio_greatest = 0;
+  cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest);
+  if ((e = cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio_greatest)) != cudaSuccess) return bail("cudaStreamCreate", e);
+  if ((e = cudaStreamCreateWithPriority(&c->rstream, cudaStreamNonBlocking, prio_least)) != cudaSuccess) return bail("cudaStreamCreate", e);
   if ((e = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
-  if ((e = cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+  c->slot[0].index = 0;
+  c->slot[1].index = 1;
+  if ((e = cudaStreamCreateWithPriority(&c->aux_stream, cudaStreamNonBlocking, prio_greatest)) != cudaSuccess) return bail("cudaStreamCreate", e);
   for (int i = 0; i < 2; ++i) {
     if ((e = cudaEventCreateWithFlags(&c->ev_fork[i], cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
     if ((e = cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
@@ -194,6 +206,8 @@ extern "C" int gs_create(int device_ordinal, gs_context **out_ctx) {
     for (auto &ev : sl.evp)
       if ((e = cudaEventCreate(&ev)) != cudaSuccess) return bail("cudaEventCreate", e);
     if ((e = cudaEventCreateWithFlags(&sl.ev_done, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
+    if ((e = cudaEventCreateWithFlags(&sl.ev_binned, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
+    if ((e = cudaEventCreate(&sl.ev_r0)) != cudaSuccess) return bail("cudaEventCreate", e);
     if ((e = cudaEventCreateWithFlags(&sl.ev_copied, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
     if ((e = cudaMalloc((void **)&sl.ctr, sizeof(FrameCounters))) != cudaSuccess) return bail("cudaMalloc", e);
     if ((e = cudaMalloc((void **)&sl.fp, sizeof(FrameParams))) != cudaSuccess) return bail("cudaMalloc", e);
@@ -223,10 +237,12 @@ extern "C" int gs_destroy(gs_context *c) {
   if (!c) return GS_OK;
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
+  if (c->rstream) cudaStreamSynchronize(c->rstream);
   dev_free(c->center_scale); dev_free(c->cov_color); dev_free(c->size_alpha);
   dev_free(c->depth); dev_free(c->idx_a); dev_free(c->dig_a); dev_free(c->order); dev_free(c->proj_rec); dev_free(c->rect);
-  dev_free(c->inst_tile); dev_free(c->inst_idx); dev_free(c->inst_dig_b); dev_free(c->inst_idx_b); dev_free(c->inst_rec);
-  dev_free(c->tile_count); dev_free(c->tile_start); dev_free(c->quirk_table);
+  dev_free(c->inst_tile); dev_free(c->inst_idx); dev_free(c->inst_dig_b); dev_free(c->inst_idx_b);
+  dev_free(c->inst_rec[0]); dev_free(c->inst_rec[1]);
+  dev_free(c->tile_count); dev_free(c->tile_start[0]); dev_free(c->tile_start[1]); dev_free(c->quirk_table);
   if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
   drop_graphs(c);
   dev_free(c->table_n); dev_free(c->table_d); dev_free(c->tile_total); dev_free(c->totals); dev_free(c->sort_hdr);
@@ -239,6 +255,8 @@ extern "C" int gs_destroy(gs_context *c) {
     for (auto &ev : sl.ev) if (ev) cudaEventDestroy(ev);
     for (auto &ev : sl.evp) if (ev) cudaEventDestroy(ev);
     if (sl.ev_done) cudaEventDestroy(sl.ev_done);
+    if (sl.ev_binned) cudaEventDestroy(sl.ev_binned);
+    if (sl.ev_r0) cudaEventDestroy(sl.ev_r0);
     if (sl.ev_copied) cudaEventDestroy(sl.ev_copied);
   }
   for (auto &ev : c->ev)
@@ -248,6 +266,7 @@ extern "C" int gs_destroy(gs_context *c) {
     if (c->ev_join[i]) cudaEventDestroy(c->ev_join[i]);
   }
   if (c->aux_stream) cudaStreamDestroy(c->aux_stream);
+  if (c->rstream) cudaStreamDestroy(c->rstream);
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
@@ -407,7 +426,9 @@ extern "C" uint32_t gs_owned_tiles(uint32_t width, uint32_t height, uint32_t ran
 
 // Everything one frame does on the main stream; all per-frame inputs come from sl.fp (device memory), so the same
 // sequence can be captured once into a CUDA graph and replayed.
-static cudaError_t enqueue_frame(gs_context *c, gs_context::Slot &sl, bool reuse, uint32_t n_tiles, bool external_events) {
+// The part of a frame that runs on the main stream: sort, projection, binning.  All per-frame inputs come from
+// sl.fp (device memory), so the sequence is captured once into a CUDA graph and replayed.
+static cudaError_t enqueue_main(gs_context *c, gs_context::Slot &sl, bool reuse, uint32_t n_tiles, bool external_events) {
   auto rec = [&](cudaEvent_t ev, cudaStream_t st) {
     return external_events ? cudaEventRecordWithFlags(ev, st, cudaEventRecordExternal) : cudaEventRecord(ev, st);
   };
@@ -443,33 +464,37 @@ static cudaError_t enqueue_frame(gs_context *c, gs_context::Slot &sl, bool reuse
   // fork 2: the tile-range scan only needs the tile counts of k_emit; it runs beside the tile radix passes
   if ((e = cudaEventRecord(c->ev_fork[1], m))) return e;
   if ((e = cudaStreamWaitEvent(x, c->ev_fork[1], 0))) return e;
-  launch_tile_scan(c, n_tiles, x);
+  launch_tile_scan(c, n_tiles, c->tile_start[sl.index], x);
   if ((e = cudaEventRecord(c->ev_join[1], x))) return e;
-  launch_tile_radix(c, sl.ctr);
+  launch_tile_radix(c, sl.ctr, c->inst_rec[sl.index]);
   if ((e = cudaStreamWaitEvent(m, c->ev_join[1], 0))) return e;
   if ((e = rec(sl.ev[3], m))) return e;
-  launch_raster(c, sl.fp, n_tiles);
-  launches += 11;
-  if ((e = rec(sl.ev[4], m))) return e;
-  sl.launches = launches;
+  launches += 10;
+  sl.launches = launches + 1;
   return cudaGetLastError();
 }
 
-static int launch_frame(gs_context *c, gs_context::Slot &sl, bool reuse, uint32_t n_tiles) {
-  // (re)capture when anything baked into the launches changed
-  gs_context::GraphKey k;
-  k.n = c->n; k.n_tiles = n_tiles; k.cap_inst = c->cap_inst; k.p0 = c->depth; k.p1 = c->inst_rec; k.p2 = c->center_scale;
-  if (memcmp(&k, &c->gkey, sizeof(k)) != 0) {
-    drop_graphs(c);
-    c->gkey = k;
-  }
+// The raster of a frame, on the raster stream: it only reads this slot's inst_rec / tile_start, so the next
+// frame's sort + binning (main stream, other slot) runs underneath it.
+static cudaError_t enqueue_raster(gs_context *c, gs_context::Slot &sl, uint32_t n_tiles, bool external_events) {
+  auto rec = [&](cudaEvent_t ev, cudaStream_t st) {
+    return external_events ? cudaEventRecordWithFlags(ev, st, cudaEventRecordExternal) : cudaEventRecord(ev, st);
+  };
+  cudaError_t e;
+  if ((e = rec(sl.ev_r0, c->rstream))) return e;
+  launch_raster(c, sl.fp, n_tiles, c->inst_rec[sl.index], c->tile_start[sl.index], c->rstream);
+  if ((e = rec(sl.ev[4], c->rstream))) return e;
+  return cudaGetLastError();
+}
+
+template <class F>
+static int run_graph(gs_context *c, cudaGraphExec_t &ge, cudaStream_t stream, F enqueue) {
   if (c->use_graphs) {
-    cudaGraphExec_t &ge = sl.graph[reuse ? 1 : 0];
     if (!ge) {
       cudaGraph_t g = nullptr;
-      GS_CUDA(c, cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
-      cudaError_t e = enqueue_frame(c, sl, reuse, n_tiles, true);
-      cudaError_t e2 = cudaStreamEndCapture(c->stream, &g);
+      GS_CUDA(c, cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+      cudaError_t e = enqueue(true);
+      cudaError_t e2 = cudaStreamEndCapture(stream, &g);
       if (e != cudaSuccess || e2 != cudaSuccess || !g) {
         if (g) cudaGraphDestroy(g);
         cudaGetLastError();
@@ -481,18 +506,35 @@ static int launch_frame(gs_context *c, gs_context::Slot &sl, bool reuse, uint32_
       }
     }
     if (ge) {
-      GS_CUDA(c, cudaGraphLaunch(ge, c->stream));
+      GS_CUDA(c, cudaGraphLaunch(ge, stream));
       return GS_OK;
     }
   }
-  GS_CUDA(c, enqueue_frame(c, sl, reuse, n_tiles, false));
+  GS_CUDA(c, enqueue(false));
   return GS_OK;
+}
+
+static int launch_frame(gs_context *c, gs_context::Slot &sl, bool reuse, uint32_t n_tiles) {
+  // (re)capture when anything baked into the launches changed
+  gs_context::GraphKey k;
+  k.n = c->n; k.n_tiles = n_tiles; k.cap_inst = c->cap_inst; k.p0 = c->depth; k.p1 = c->inst_rec[0]; k.p2 = c->center_scale;
+  if (memcmp(&k, &c->gkey, sizeof(k)) != 0) {
+    drop_graphs(c);
+    c->gkey = k;
+  }
+  // this slot's previous raster (two frames ago) must have finished reading inst_rec / tile_start / fp
+  GS_CUDA(c, cudaStreamWaitEvent(c->stream, sl.ev_done, 0));
+  int rc = run_graph(c, sl.graph[reuse ? 1 : 0], c->stream, [&](bool ext) { return enqueue_main(c, sl, reuse, n_tiles, ext); });
+  if (rc) return rc;
+  GS_CUDA(c, cudaEventRecord(sl.ev_binned, c->stream));
+  GS_CUDA(c, cudaStreamWaitEvent(c->rstream, sl.ev_binned, 0));
+  return run_graph(c, sl.graph_r, c->rstream, [&](bool ext) { return enqueue_raster(c, sl, n_tiles, ext); });
 }
 
 // after the frame's kernels: counters (and the frame, when the caller's buffer is host memory) go to the host on
 // the copy stream, so the next frame's kernels overlap the PCIe transfer
 static int enqueue_readback(gs_context *c, gs_context::Slot &sl) {
-  GS_CUDA(c, cudaEventRecord(sl.ev_done, c->stream));
+  GS_CUDA(c, cudaEventRecord(sl.ev_done, c->rstream));
   GS_CUDA(c, cudaStreamWaitEvent(c->copy_stream, sl.ev_done, 0));
   GS_CUDA(c, cudaMemcpyAsync(sl.ctr_host, sl.ctr, sizeof(FrameCounters), cudaMemcpyDeviceToHost, c->copy_stream));
   if (sl.host_out)
@@ -555,6 +597,7 @@ static int wait_slot(gs_context *c, gs_context::Slot &sl, gs_stats *stats) {
     // instance buffer too small: grow to the measured demand and run this frame again
     const uint64_t need = std::max<uint64_t>(sl.ctr_host->n_inst + sl.ctr_host->n_inst / 8, c->cap_inst * 2);
     GS_CUDA(c, cudaStreamSynchronize(c->stream));  // the other slot's frame may still be using the buffers
+    GS_CUDA(c, cudaStreamSynchronize(c->rstream));
     int rcode = ensure_instances(c, need);
     if (rcode) return rcode;
     if ((rcode = submit(c, sl))) return rcode;
@@ -568,7 +611,7 @@ static int wait_slot(gs_context *c, gs_context::Slot &sl, gs_stats *stats) {
   cudaEventElapsedTime(&c->stats.ms_sort, sl.ev[0], sl.ev[1]);
   cudaEventElapsedTime(&c->stats.ms_project, sl.evp[0], sl.evp[1]);  // on the aux stream, overlapping the sort
   cudaEventElapsedTime(&c->stats.ms_bin, sl.ev[2], sl.ev[3]);
-  cudaEventElapsedTime(&c->stats.ms_raster, sl.ev[3], sl.ev[4]);
+  cudaEventElapsedTime(&c->stats.ms_raster, sl.ev_r0, sl.ev[4]);
   cudaEventElapsedTime(&c->stats.ms_total, sl.ev[0], sl.ev[4]);
   c->order_count = sl.ctr_host->n_valid;
   if (stats) *stats = c->stats;
@@ -593,6 +636,7 @@ extern "C" int gs_render_async(gs_context *c, const gs_render_params *p, void *o
   if (grow) {
     if ((rcode = drain(c))) return rcode;
     GS_CUDA(c, cudaStreamSynchronize(c->stream));
+    GS_CUDA(c, cudaStreamSynchronize(c->rstream));
     if ((rcode = ensure_scratch(c))) return rcode;
     if ((rcode = ensure_tiles(c, n_tiles))) return rcode;
     if (c->cap_inst == 0 && (rcode = ensure_instances(c, std::max<uint64_t>(1u << 20, (uint64_t)c->n * 4)))) return rcode;
@@ -685,14 +729,16 @@ extern "C" int gs_host_free(gs_context *c, void *p) {
 extern "C" int gs_memcpy_d2h(gs_context *c, void *dst, const void *src, size_t bytes) {
   if (!c || !dst || !src) return GS_ERR_INVALID;
   GS_CUDA(c, cudaSetDevice(c->device));
-  GS_CUDA(c, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream));
-  GS_CUDA(c, cudaStreamSynchronize(c->stream));
+  GS_CUDA(c, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->rstream));
+  GS_CUDA(c, cudaStreamSynchronize(c->rstream));
   return GS_OK;
 }
-extern "C" void *gs_stream(gs_context *c) { return c ? (void *)c->stream : nullptr; }
+// frames complete on the raster stream: external work ordered after a frame (collectives, copies) goes there
+extern "C" void *gs_stream(gs_context *c) { return c ? (void *)c->rstream : nullptr; }
 extern "C" int gs_synchronize(gs_context *c) {
   if (!c) return GS_ERR_INVALID;
   GS_CUDA(c, cudaSetDevice(c->device));
   GS_CUDA(c, cudaStreamSynchronize(c->stream));
+  GS_CUDA(c, cudaStreamSynchronize(c->rstream));
   return GS_OK;
 }

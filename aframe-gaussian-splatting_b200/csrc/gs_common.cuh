@@ -120,14 +120,15 @@ struct gs_context {
   uint32_t *inst_idx = nullptr;
   uint8_t *inst_dig_b = nullptr;
   uint32_t *inst_idx_b = nullptr;
-  float4 *inst_rec = nullptr;    // 2 x float4 per instance, sorted by (tile, draw order)
+  float4 *inst_rec[2] = {nullptr, nullptr};  // 2 x float4 per instance, sorted by (tile, draw order); one per slot:
+                                             // the raster of frame k reads [k&1] while frame k+1 is binned into the other
   uint32_t *table_d = nullptr;   // radix chunk histograms of the tile passes [256][table_d_stride]
   uint32_t table_d_stride = 0;
 
   // ---- per-frame tables ----
   uint32_t tiles_cap = 0;
   uint32_t *tile_count = nullptr;  // [T]
-  uint32_t *tile_start = nullptr;  // [T+1]
+  uint32_t *tile_start[2] = {nullptr, nullptr};  // [T+1], one per slot (read by the raster)
   double *quirk_table = nullptr;   // parseInt quirk thresholds (device)
   int quirk_n = 0;
   gs::SortHeader *sort_hdr = nullptr;  // device: counters header of the last sort (for GS_RENDER_REUSE_SORT)
@@ -143,7 +144,11 @@ struct gs_context {
     cudaEvent_t ev[5]{};                     // stage boundaries (timing)
     cudaEvent_t evp[2]{};                    // k_project on the aux stream (timing)
     cudaEvent_t ev_done = nullptr, ev_copied = nullptr;
-    cudaGraphExec_t graph[2] = {nullptr, nullptr};  // [reuse_sort]
+    cudaGraphExec_t graph[2] = {nullptr, nullptr};  // sort+project+bin on the main stream, [reuse_sort]
+    cudaGraphExec_t graph_r = nullptr;              // raster on the raster stream
+    cudaEvent_t ev_binned = nullptr;                // main-stream part of this slot's frame finished
+    cudaEvent_t ev_r0 = nullptr;                    // raster start (timing)
+    int index = 0;
     bool pending = false;
     bool host_out = false;
     void *out_user = nullptr;
@@ -152,6 +157,7 @@ struct gs_context {
     uint32_t launches = 0;
   } slot[2];
   uint64_t next_ticket = 0;
+  cudaStream_t rstream = nullptr;   // raster stream: frame k is rasterised here while frame k+1 is sorted / binned
   cudaStream_t copy_stream = nullptr;
   cudaStream_t aux_stream = nullptr;             // runs k_project / k_tile_scan beside the radix passes
   cudaEvent_t ev_fork[2]{}, ev_join[2]{};
@@ -174,9 +180,10 @@ void launch_depth_radix(gs_context *c, FrameCounters *ctr);  // 6 launches -> c-
 void launch_pack(gs_context *c, const uint8_t *rows_dev, uint32_t first, uint32_t n);
 void launch_project(gs_context *c, const FrameParams *fp, cudaStream_t stream);
 void launch_emit(gs_context *c, const FrameParams *fp, FrameCounters *ctr);  // 2 launches
-void launch_tile_radix(gs_context *c, FrameCounters *ctr);                   // 6 launches
-void launch_tile_scan(gs_context *c, uint32_t n_tiles, cudaStream_t stream);
-void launch_raster(gs_context *c, const FrameParams *fp, uint32_t n_tiles);
+void launch_tile_radix(gs_context *c, FrameCounters *ctr, float4 *inst_rec_out);  // 6 launches
+void launch_tile_scan(gs_context *c, uint32_t n_tiles, uint32_t *tile_start_out, cudaStream_t stream);
+void launch_raster(gs_context *c, const FrameParams *fp, uint32_t n_tiles, const float4 *inst_rec,
+                   const uint32_t *tile_start, cudaStream_t stream);
 void launch_assemble(gs_context *c, const void *gathered, uint32_t tiles_per_rank, uint32_t world, uint32_t width,
                      uint32_t height, int32_t format, void *out_frame);
 

@@ -498,8 +498,8 @@ void launch_emit(gs_context *c, const FrameParams *fp, FrameCounters *ctr) {
                                                     c->inst_tile, c->inst_idx, c->tile_count, ctr);
 }
 
-void launch_tile_scan(gs_context *c, uint32_t n_tiles, cudaStream_t stream) {
-  k_tile_scan<<<1, 1024, 0, stream>>>(c->tile_count, n_tiles, c->tile_start);
+void launch_tile_scan(gs_context *c, uint32_t n_tiles, uint32_t *tile_start_out, cudaStream_t stream) {
+  k_tile_scan<<<1, 1024, 0, stream>>>(c->tile_count, n_tiles, tile_start_out);
 }
 
 }  // namespace gs

@@ -187,14 +187,15 @@ __global__ void __launch_bounds__(256) k_assemble(const void *__restrict__ gathe
   else ((float4 *)out)[dst] = ((const float4 *)gathered)[src];
 }
 
-void launch_raster(gs_context *c, const FrameParams *fp, uint32_t n_tiles) {
-  k_raster<<<n_tiles, 256, 0, c->stream>>>(c->inst_rec, c->tile_start, fp);
+void launch_raster(gs_context *c, const FrameParams *fp, uint32_t n_tiles, const float4 *inst_rec,
+                   const uint32_t *tile_start, cudaStream_t stream) {
+  k_raster<<<n_tiles, 256, 0, stream>>>(inst_rec, tile_start, fp);
 }
 
 void launch_assemble(gs_context *c, const void *gathered, uint32_t tiles_per_rank, uint32_t world, uint32_t width,
                      uint32_t height, int32_t format, void *out_frame) {
   const uint32_t tiles_x = (width + kTile - 1) / kTile, tiles_y = (height + kTile - 1) / kTile;
-  k_assemble<<<tiles_x * tiles_y, 256, 0, c->stream>>>(gathered, tiles_per_rank, world, width, height, format, out_frame);
+  k_assemble<<<tiles_x * tiles_y, 256, 0, c->rstream>>>(gathered, tiles_per_rank, world, width, height, format, out_frame);
 }
 
 uint32_t owned_tiles_host(uint32_t width, uint32_t height, uint32_t rank, uint32_t world) {

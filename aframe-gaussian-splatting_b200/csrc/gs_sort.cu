@@ -415,7 +415,7 @@ static RadixArgs make_args(gs_context *c, FrameCounters *ctr) {
   a.inst_dig_b = c->inst_dig_b;
   a.inst_idx_b = c->inst_idx_b;
   a.proj_rec = c->proj_rec;
-  a.inst_rec = c->inst_rec;
+  a.inst_rec = nullptr;
   return a;
 }
 
@@ -438,8 +438,9 @@ void launch_depth_radix(gs_context *c, FrameCounters *ctr) {
 }
 
 // stable sort of the tile instances by tile id (6 launches); T2 writes the per-tile record lists
-void launch_tile_radix(gs_context *c, FrameCounters *ctr) {
+void launch_tile_radix(gs_context *c, FrameCounters *ctr, float4 *inst_rec_out) {
   RadixArgs a = make_args(c, ctr);
+  a.inst_rec = inst_rec_out;
   a.table = c->table_d;
   a.totals = c->totals + 256;
   a.stride = c->table_d_stride;

@@ -10,8 +10,8 @@ N = 1 workload = BASELINE.json configs[1]: train-like 1 M synthetic splats, 1920
 N > 1: the same scene, the FRAME sharded by 16x16 screen tile over the ranks (every rank holds the full
 splat table and the full draw order), one NCCL all-gather of finished RGBA8 tiles per frame -> strong scaling.
 
-`value` : frames/s with the scene resident in HBM and the frame left in HBM (device-timed, CUDA events on the
-          library's stream, L2 flushed between steps).
+`value` : frames/s with the scene resident in HBM and the frame left in HBM (device-timed: one CUDA-event pair around
+          the K steps on the library's stream, two frames in flight, L2 flushed between steps inside the region).
 `e2e`   : frames/s through gs_render with HOST buffers: camera matrices in, RGBA8 frame out to pinned host memory,
           both copies inside the timed region.
 """
@@ -269,15 +269,25 @@ def run_ours(args):
     # ---- value: device-resident frames ----
     stats = []
     barrier()
-    t_dev, _ = run_pipeline(submit_device, args.steps, stats)
+    # whole-region time (one CUDA-event pair around all K steps, L2 flushes included): with two frames in flight the
+    # per-step pairs only see the raster stream and would hide the sort/bin work overlapped on the other stream
+    _, total_ms = run_pipeline(submit_device, args.steps, stats)
     barrier()
-    total_ms = float(sum(t_dev))
+    total_ms = float(total_ms)
     if world > 1:
         t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total_ms = float(t.item())
     ms_per_step = total_ms / args.steps
     fps = 1000.0 / ms_per_step
+
+    # ---- un-overlapped frames (one in flight) for the per-stage / roofline numbers: with two frames in flight the
+    #      stages of consecutive frames run concurrently and their individual durations stretch ----
+    lat_stats = []
+    for i in range(max(5, min(args.steps, 20))):
+        with torch.cuda.stream(stream):
+            flush.zero_()
+        lat_stats.append(ctx.wait(submit_device(i)).as_dict())
 
     # ---- e2e: host buffers through the public C-ABI call, copies inside the timed region ----
     host_frames = [ctx.pinned_array((h, w, 4), np.uint8), ctx.pinned_array((h, w, 4), np.uint8)]
@@ -324,9 +334,9 @@ def run_ours(args):
     clocks = sampler.stop() if sampler is not None else None
 
     if rank == 0:
-        st = {k: float(np.mean([s[k] for s in stats])) for k in stats[0]}
+        st = {k: float(np.mean([s[k] for s in lat_stats])) for k in lat_stats[0]}
         for k in ("n_splats", "n_sorted", "n_visible", "n_instances", "n_instances_kept", "n_tiles", "width", "height", "kernel_launches", "n_dropped"):
-            st[k] = int(stats[0][k])
+            st[k] = int(lat_stats[0][k])
         peak, peak_src = load_peaks()
         ab = algorithmic_bytes(st)
         stage_ms = {"sort": st["ms_sort"], "project": st["ms_project"], "bin": st["ms_bin"], "raster": st["ms_raster"]}
@@ -349,7 +359,7 @@ def run_ours(args):
             "dtype": "f64 sort keys + f32 shading", "data": "synthetic",
             "config": {"workload": args.workload, "n_splats": n, "width": w, "height": h, "camera": "fixed",
                        "parallelism": "1 GPU" if world == 1 else f"screen-tile sharding x{world} + NCCL all-gather of RGBA8 tiles",
-                       "l2": "flushed between timed steps (160 MiB memset outside the event pair)",
+                       "l2": "flushed between timed steps (160 MiB memset on the raster stream, INSIDE the timed region)",
                        "counters": {k: st[k] for k in ("n_splats", "n_sorted", "n_visible", "n_instances", "n_instances_kept", "n_tiles")}},
             "msplats_per_s": n * fps / 1e6,
             "e2e": e2e,
@@ -362,6 +372,9 @@ def run_ours(args):
                          "algorithmic_bytes_per_launch": ab[dom], "ms_per_launch": stage_ms[dom],
                          "note": "k_raster is FP32-ALU bound (one exp + ~12 FMA per pixel-splat pair), reported against HBM as SURVEY.md 8d prescribes"},
             "stages": {k: roof(k) for k in stage_ms},
+            "pipeline": "two frames in flight: frame k is rasterised (low-priority stream) while frame k+1 is sorted and binned "
+                        "(high-priority stream); ms_per_step is the steady-state frame period, stages/roofline/frame are from "
+                        "un-overlapped frames (one in flight) timed with the same CUDA events",
             "frame": {"bytes": ab["total"], "ms_device": st["ms_total"], "achieved_gbs": ab["total"] / (st["ms_total"] * 1e-3) / 1e9,
                       "frac": ab["total"] / (st["ms_total"] * 1e-3) / 1e9 / peak},
         }

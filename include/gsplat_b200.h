@@ -75,7 +75,8 @@ typedef struct gs_stats {
                               passes on a second stream: overlaps ms_sort)                    */
   float ms_bin;            /* instance emission + two tile-radix passes                      */
   float ms_raster;         /* tile raster + composite                                        */
-  float ms_total;          /* whole frame on the device (events on the context's stream)     */
+  float ms_total;          /* first kernel to last kernel of this frame on the device; with two
+                              frames in flight it includes waiting behind the previous raster  */
   uint32_t kernel_launches;/* kernels launched by the call                                   */
   uint32_t n_instances_kept;/* D  tile instances whose tile really meets the r<=2 footprint    */
 } gs_stats;
@@ -189,7 +190,9 @@ GS_API int gs_device_free(gs_context *ctx, void *dev_ptr);
 GS_API int gs_host_alloc(gs_context *ctx, size_t bytes, void **out_host_ptr);
 GS_API int gs_host_free(gs_context *ctx, void *host_ptr);
 GS_API int gs_memcpy_d2h(gs_context *ctx, void *dst_host, const void *src_dev, size_t bytes);
-/* The CUDA stream (cudaStream_t) all work of this context is issued on. */
+/* The CUDA stream (cudaStream_t) on which frames COMPLETE (the raster stream): work enqueued there after
+ * gs_render_async (collectives, copies, gs_assemble_tiles) is ordered after that frame.  Sort + binning of the
+ * next frame run on an internal second stream underneath the raster. */
 GS_API void *gs_stream(gs_context *ctx);
 GS_API int gs_synchronize(gs_context *ctx);
 
