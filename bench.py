@@ -188,8 +188,7 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # keep stdout to the one JSON line
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU path")
@@ -322,15 +321,10 @@ def run_ours(args):
     def step_device():
         ctx.wait(submit_device(0))
 
-    # keep the GPU loaded long enough for nvidia-smi to observe the clocks under this workload
-    if sampler is not None:
-        t_end = time.time() + 1.2
-        while time.time() < t_end:
-            step_device()
-    elif world > 1:
-        t_end = time.time() + 1.2
-        while time.time() < t_end:
-            step_device()
+    # keep the GPU loaded long enough for nvidia-smi to observe the clocks under this workload.  The iteration count
+    # is derived from the all-reduced step time, so every rank issues the same number of collectives.
+    for _ in range(int(min(4000, max(10, 1200.0 / max(ms_per_step, 1e-3))))):
+        step_device()
     clocks = sampler.stop() if sampler is not None else None
 
     if rank == 0:
