@@ -85,9 +85,37 @@ def report(src, dst, traffic_key=None):
     print(open(dst).read())
 
 
+def stage_traffic(src, key, pattern, dst_dir):
+    """Sum of mean DRAM bytes (read + write) per launch over the kernels whose name matches `pattern`
+    (one frame's worth of a multi-kernel stage) -> profiles/traffic.json[key]."""
+    import re
+    out = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr, units = rows[0], rows[1]
+    ik, ir, iw = hdr.index("Kernel Name"), hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+    mult = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    per = collections.OrderedDict()
+    for r in rows[2:]:
+        name = r[ik].split("(gs::")[0].split("(const")[0].strip()
+        if not re.search(pattern, name):
+            continue
+        b = float(r[ir].replace(",", "")) * mult[units[ir]] + float(r[iw].replace(",", "")) * mult[units[iw]]
+        per.setdefault(name, []).append(b)
+    total = sum(sum(v) / len(v) for v in per.values())
+    tp = os.path.join(dst_dir, "traffic.json")
+    cur = json.load(open(tp)) if os.path.exists(tp) else {}
+    cur[key] = total
+    json.dump(cur, open(tp, "w"), indent=1)
+    for k, v in per.items():
+        print(f"{k:40s} {sum(v)/len(v)/1e6:8.1f} MB x{len(v)}")
+    print(f"{key}: {total/1e6:.1f} MB per frame")
+
+
 if __name__ == "__main__":
     if sys.argv[1] == "launches":
         launches(sys.argv[2], sys.argv[3])
+    elif sys.argv[1] == "stage":
+        stage_traffic(sys.argv[2], sys.argv[3], sys.argv[4], sys.argv[5])
     else:
         tk = sys.argv[sys.argv.index("--traffic-key") + 1] if "--traffic-key" in sys.argv else None
         report(sys.argv[2], sys.argv[3], tk)
