@@ -103,14 +103,15 @@ static int ensure_scratch(gs_context *c) {
 static int ensure_instances(gs_context *c, uint64_t need) {
   if (need <= c->cap_inst && c->inst_rec[0]) return GS_OK;
   if (need >= (1ull << 30)) return fail(c, GS_ERR_CAPACITY, "more than 2^30 tile instances in one frame");
-  dev_free(c->inst_tile); dev_free(c->inst_idx); dev_free(c->inst_dig_b); dev_free(c->inst_idx_b);
+  dev_free(c->inst_tile); dev_free(c->inst_idx); dev_free(c->inst_tile_b); dev_free(c->inst_tile_f); dev_free(c->inst_idx_b);
   dev_free(c->inst_rec[0]); dev_free(c->inst_rec[1]);
   dev_free(c->table_d);
-  c->table_d_stride = (uint32_t)((need + kRadixTile - 1) / kRadixTile + 1);
+  c->table_d_stride = (uint32_t)((need + kRadixTile / 2 - 1) / (kRadixTile / 2) + 2);  // one column per 2048-instance window
   GS_CUDA(c, dev_alloc(&c->table_d, (size_t)256 * c->table_d_stride));
   GS_CUDA(c, dev_alloc(&c->inst_tile, need));
   GS_CUDA(c, dev_alloc(&c->inst_idx, need));
-  GS_CUDA(c, dev_alloc(&c->inst_dig_b, need));
+  GS_CUDA(c, dev_alloc(&c->inst_tile_b, need));
+  GS_CUDA(c, dev_alloc(&c->inst_tile_f, need));
   GS_CUDA(c, dev_alloc(&c->inst_idx_b, need));
   GS_CUDA(c, dev_alloc(&c->inst_rec[0], 2 * need));
   GS_CUDA(c, dev_alloc(&c->inst_rec[1], 2 * need));
@@ -119,11 +120,10 @@ static int ensure_instances(gs_context *c, uint64_t need) {
 }
 
 static int ensure_tiles(gs_context *c, uint32_t n_tiles) {
-  if (n_tiles <= c->tiles_cap && c->tile_count) return GS_OK;
-  dev_free(c->tile_count); dev_free(c->tile_start[0]); dev_free(c->tile_start[1]);
-  GS_CUDA(c, dev_alloc(&c->tile_count, (size_t)n_tiles + 1));
-  GS_CUDA(c, dev_alloc(&c->tile_start[0], (size_t)n_tiles + 2));
-  GS_CUDA(c, dev_alloc(&c->tile_start[1], (size_t)n_tiles + 2));
+  if (n_tiles <= c->tiles_cap && c->tile_range[0]) return GS_OK;
+  dev_free(c->tile_range[0]); dev_free(c->tile_range[1]);
+  GS_CUDA(c, dev_alloc(&c->tile_range[0], (size_t)n_tiles + 1));
+  GS_CUDA(c, dev_alloc(&c->tile_range[1], (size_t)n_tiles + 1));
   c->tiles_cap = n_tiles;
   return GS_OK;
 }
@@ -240,9 +240,9 @@ extern "C" int gs_destroy(gs_context *c) {
   if (c->rstream) cudaStreamSynchronize(c->rstream);
   dev_free(c->center_scale); dev_free(c->cov_color); dev_free(c->size_alpha);
   dev_free(c->depth); dev_free(c->idx_a); dev_free(c->dig_a); dev_free(c->order); dev_free(c->proj_rec); dev_free(c->rect);
-  dev_free(c->inst_tile); dev_free(c->inst_idx); dev_free(c->inst_dig_b); dev_free(c->inst_idx_b);
+  dev_free(c->inst_tile); dev_free(c->inst_idx); dev_free(c->inst_tile_b); dev_free(c->inst_tile_f); dev_free(c->inst_idx_b);
   dev_free(c->inst_rec[0]); dev_free(c->inst_rec[1]);
-  dev_free(c->tile_count); dev_free(c->tile_start[0]); dev_free(c->tile_start[1]); dev_free(c->quirk_table);
+  dev_free(c->tile_range[0]); dev_free(c->tile_range[1]); dev_free(c->quirk_table);
   if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
   drop_graphs(c);
   dev_free(c->table_n); dev_free(c->table_d); dev_free(c->tile_total); dev_free(c->totals); dev_free(c->sort_hdr);
@@ -436,7 +436,7 @@ static cudaError_t enqueue_main(gs_context *c, gs_context::Slot &sl, bool reuse,
   cudaError_t e;
   if ((e = cudaMemcpyAsync(sl.fp, sl.fp_host, sizeof(FrameParams), cudaMemcpyHostToDevice, m))) return e;
   if ((e = cudaMemsetAsync(sl.ctr, 0, sizeof(FrameCounters), m))) return e;
-  if ((e = cudaMemsetAsync(c->tile_count, 0, sizeof(uint32_t) * ((size_t)n_tiles + 1), m))) return e;
+  if ((e = cudaMemsetAsync(c->tile_range[sl.index], 0, sizeof(uint2) * (size_t)n_tiles, m))) return e;
   if ((e = rec(sl.ev[0], m))) return e;
   uint32_t launches = 0;
   if (reuse) {
@@ -460,16 +460,11 @@ static cudaError_t enqueue_main(gs_context *c, gs_context::Slot &sl, bool reuse,
   if ((e = rec(sl.ev[1], m))) return e;
   if ((e = cudaStreamWaitEvent(m, c->ev_join[0], 0))) return e;
   if ((e = rec(sl.ev[2], m))) return e;
-  launch_emit(c, sl.fp, sl.ctr);
-  // fork 2: the tile-range scan only needs the tile counts of k_emit; it runs beside the tile radix passes
-  if ((e = cudaEventRecord(c->ev_fork[1], m))) return e;
-  if ((e = cudaStreamWaitEvent(x, c->ev_fork[1], 0))) return e;
-  launch_tile_scan(c, n_tiles, c->tile_start[sl.index], x);
-  if ((e = cudaEventRecord(c->ev_join[1], x))) return e;
-  launch_tile_radix(c, sl.ctr, c->inst_rec[sl.index]);
-  if ((e = cudaStreamWaitEvent(m, c->ev_join[1], 0))) return e;
+  launch_emit(c, sl.fp, sl.ctr);                          // 2 launches (k_emit also histograms pass T1)
+  launch_tile_radix(c, sl.ctr, c->inst_rec[sl.index]);   // 5 launches
+  launch_tile_ranges(c, sl.ctr, c->tile_range[sl.index]);
   if ((e = rec(sl.ev[3], m))) return e;
-  launches += 10;
+  launches += 9;
   sl.launches = launches + 1;
   return cudaGetLastError();
 }
@@ -482,7 +477,7 @@ static cudaError_t enqueue_raster(gs_context *c, gs_context::Slot &sl, uint32_t 
   };
   cudaError_t e;
   if ((e = rec(sl.ev_r0, c->rstream))) return e;
-  launch_raster(c, sl.fp, n_tiles, c->inst_rec[sl.index], c->tile_start[sl.index], c->rstream);
+  launch_raster(c, sl.fp, n_tiles, c->inst_rec[sl.index], c->tile_range[sl.index], c->rstream);
   if ((e = rec(sl.ev[4], c->rstream))) return e;
   return cudaGetLastError();
 }
@@ -632,7 +627,7 @@ extern "C" int gs_render_async(gs_context *c, const gs_render_params *p, void *o
   int rcode;
   if (sl.pending && (rcode = wait_slot(c, sl, nullptr))) return rcode;  // slot reuse: its previous frame must be done
   // growing any shared buffer needs an idle pipeline
-  const bool grow = !(c->scratch_cap >= c->cap && c->depth) || !(n_tiles <= c->tiles_cap && c->tile_count) || c->cap_inst == 0;
+  const bool grow = !(c->scratch_cap >= c->cap && c->depth) || !(n_tiles <= c->tiles_cap && c->tile_range[0]) || c->cap_inst == 0;
   if (grow) {
     if ((rcode = drain(c))) return rcode;
     GS_CUDA(c, cudaStreamSynchronize(c->stream));

@@ -118,7 +118,8 @@ struct gs_context {
   uint64_t cap_inst = 0;
   uint16_t *inst_tile = nullptr;
   uint32_t *inst_idx = nullptr;
-  uint8_t *inst_dig_b = nullptr;
+  uint16_t *inst_tile_b = nullptr;  // tile id carried through pass T1
+  uint16_t *inst_tile_f = nullptr;  // tile id of every instance in final (tile, draw order) order
   uint32_t *inst_idx_b = nullptr;
   float4 *inst_rec[2] = {nullptr, nullptr};  // 2 x float4 per instance, sorted by (tile, draw order); one per slot:
                                              // the raster of frame k reads [k&1] while frame k+1 is binned into the other
@@ -127,8 +128,7 @@ struct gs_context {
 
   // ---- per-frame tables ----
   uint32_t tiles_cap = 0;
-  uint32_t *tile_count = nullptr;  // [T]
-  uint32_t *tile_start[2] = {nullptr, nullptr};  // [T+1], one per slot (read by the raster)
+  uint2 *tile_range[2] = {nullptr, nullptr};  // [T] {start, end} into inst_rec, one per slot (read by the raster)
   double *quirk_table = nullptr;   // parseInt quirk thresholds (device)
   int quirk_n = 0;
   gs::SortHeader *sort_hdr = nullptr;  // device: counters header of the last sort (for GS_RENDER_REUSE_SORT)
@@ -159,7 +159,7 @@ struct gs_context {
   uint64_t next_ticket = 0;
   cudaStream_t rstream = nullptr;   // raster stream: frame k is rasterised here while frame k+1 is sorted / binned
   cudaStream_t copy_stream = nullptr;
-  cudaStream_t aux_stream = nullptr;             // runs k_project / k_tile_scan beside the radix passes
+  cudaStream_t aux_stream = nullptr;             // runs k_project beside the depth radix passes
   cudaEvent_t ev_fork[2]{}, ev_join[2]{};
   bool use_graphs = true;
   // graph cache key: anything baked into the captured launches
@@ -180,10 +180,10 @@ void launch_depth_radix(gs_context *c, FrameCounters *ctr);  // 6 launches -> c-
 void launch_pack(gs_context *c, const uint8_t *rows_dev, uint32_t first, uint32_t n);
 void launch_project(gs_context *c, const FrameParams *fp, cudaStream_t stream);
 void launch_emit(gs_context *c, const FrameParams *fp, FrameCounters *ctr);  // 2 launches
-void launch_tile_radix(gs_context *c, FrameCounters *ctr, float4 *inst_rec_out);  // 6 launches
-void launch_tile_scan(gs_context *c, uint32_t n_tiles, uint32_t *tile_start_out, cudaStream_t stream);
+void launch_tile_radix(gs_context *c, FrameCounters *ctr, float4 *inst_rec_out);  // 5 launches (T1 histogram comes from k_emit)
+void launch_tile_ranges(gs_context *c, FrameCounters *ctr, uint2 *tile_range_out);
 void launch_raster(gs_context *c, const FrameParams *fp, uint32_t n_tiles, const float4 *inst_rec,
-                   const uint32_t *tile_start, cudaStream_t stream);
+                   const uint2 *tile_range, cudaStream_t stream);
 void launch_assemble(gs_context *c, const void *gathered, uint32_t tiles_per_rank, uint32_t world, uint32_t width,
                      uint32_t height, int32_t format, void *out_frame);
 

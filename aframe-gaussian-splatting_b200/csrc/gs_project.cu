@@ -7,7 +7,7 @@
 //                per slice: total; last CTA: prefix over the slices + frame total D.
 //   k_emit     : one CTA per window of 2048 instance positions -> writes (tile, splat) instances in draw order, so
 //                that a STABLE sort by tile id alone reproduces the reference's back-to-front order inside every tile.
-//   k_tile_scan: exclusive scan of the per-tile instance counts -> tile ranges for the raster.
+//                k_emit also produces pass T1's per-window digit histograms (table[digit][window]).
 #include "gs_common.cuh"
 
 namespace gs {
@@ -280,7 +280,8 @@ __global__ void __launch_bounds__(kEmitThreads, 4) k_emit(const uint2 *__restric
                                                           const float4 *__restrict__ proj_rec,
                                                           const FrameParams *__restrict__ fp, uint64_t cap_inst,
                                                           uint16_t *__restrict__ inst_tile, uint32_t *__restrict__ inst_idx,
-                                                          uint32_t *__restrict__ tile_count, FrameCounters *ctr) {
+                                                          uint32_t *__restrict__ table_t1, uint32_t table_stride,
+                                                          FrameCounters *ctr) {
   const RenderConsts &rc = fp->rc;
   __shared__ uint32_t s_wi[kEmitThreads * (kEmitPerThread + 1)];  // stride 9: conflict-free staging
   __shared__ uint16_t s_wt[kEmitThreads * (kEmitPerThread + 1)];
@@ -289,7 +290,9 @@ __global__ void __launch_bounds__(kEmitThreads, 4) k_emit(const uint2 *__restric
   __shared__ float4 s_g0[kEmitEnt];         // cx, cy, a1x, a1y
   __shared__ float2 s_g1[kEmitEnt];         // a2x, a2y
   __shared__ uint32_t s_jfl[2];
+  __shared__ uint32_t s_hist[256];  // low tile-id byte of the kept instances of this window: pass T1's histogram column
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  s_hist[tid] = 0;
   const uint32_t nv = ctr->n_valid;
   const uint32_t num_slices = (nv + kEmitTile - 1) / kEmitTile;
   const unsigned long long d_all = ctr->n_inst;
@@ -303,6 +306,7 @@ __global__ void __launch_bounds__(kEmitThreads, 4) k_emit(const uint2 *__restric
     return j < nv ? __ldg(slice_prefix + (j >> 8)) + __ldg(ent_off + j) : total;
   };
   static_assert(kEmitTile == 256, "entry -> slice is j >> 8");
+  static_assert(kEmitThreads == 256 && kEmitWindow * 2 == kRadixTile, "one histogram column per window, two per radix chunk");
 
   for (uint32_t win = blockIdx.x; win < num_windows; win += gridDim.x) {
     const uint32_t wb = win * kEmitWindow, we = min(wb + (uint32_t)kEmitWindow, total);
@@ -418,9 +422,7 @@ __global__ void __launch_bounds__(kEmitThreads, 4) k_emit(const uint2 *__restric
           uint32_t t = kNoTile;
           if (keep) {
             t = ty * rc.tiles_x + tx;
-#ifndef GS_EXP_NO_ATOMIC
-            atomicAdd(tile_count + t, 1u);
-#endif
+            atomicAdd(&s_hist[t & 255u], 1u);
           }
           const uint32_t q = p - wb;  // window-relative position
           const uint32_t si = (q / kEmitPerThread) * (kEmitPerThread + 1) + (q % kEmitPerThread);
@@ -443,37 +445,10 @@ __global__ void __launch_bounds__(kEmitThreads, 4) k_emit(const uint2 *__restric
       inst_tile[(size_t)wb + i] = s_wt[si];
       inst_idx[(size_t)wb + i] = s_wi[si];
     }
+    table_t1[(size_t)tid * table_stride + win] = s_hist[tid];  // kEmitThreads == 256 digits
+    s_hist[tid] = 0;
     __syncthreads();
   }
-}
-
-// exclusive scan of tile_count[T] -> tile_start[T+1]; one CTA
-__global__ void __launch_bounds__(1024) k_tile_scan(const uint32_t *__restrict__ tile_count, uint32_t n_tiles,
-                                                    uint32_t *__restrict__ tile_start) {
-  __shared__ uint32_t s_warp[32];
-  __shared__ uint32_t s_carry;
-  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid == 0) s_carry = 0;
-  __syncthreads();
-  for (uint32_t b = 0; b < n_tiles; b += 1024) {
-    const uint32_t i = b + tid;
-    const uint32_t v = (i < n_tiles) ? tile_count[i] : 0u;
-    uint32_t incl = v;
-    for (int o = 1; o < 32; o <<= 1) {
-      const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= (uint32_t)o) incl += t;
-    }
-    if (lane == 31) s_warp[warp] = incl;
-    __syncthreads();
-    uint32_t wbase = 0;
-    for (uint32_t k = 0; k < warp; ++k) wbase += s_warp[k];
-    const uint32_t carry = s_carry;
-    if (i < n_tiles) tile_start[i] = carry + wbase + incl - v;
-    __syncthreads();
-    if (tid == 1023) s_carry = carry + wbase + incl;
-    __syncthreads();
-  }
-  if (tid == 0) tile_start[n_tiles] = s_carry;
 }
 
 void launch_project(gs_context *c, const FrameParams *fp, cudaStream_t stream) {
@@ -495,11 +470,7 @@ void launch_emit(gs_context *c, const FrameParams *fp, FrameCounters *ctr) {
   if (wins > (uint64_t)c->sm_count * 4) wins = (uint64_t)c->sm_count * 4;
   if (wins < 1) wins = 1;
   k_emit<<<(int)wins, kEmitThreads, 0, c->stream>>>(c->ent, c->ent_off, c->slice_prefix, c->proj_rec, fp, c->cap_inst,
-                                                    c->inst_tile, c->inst_idx, c->tile_count, ctr);
-}
-
-void launch_tile_scan(gs_context *c, uint32_t n_tiles, uint32_t *tile_start_out, cudaStream_t stream) {
-  k_tile_scan<<<1, 1024, 0, stream>>>(c->tile_count, n_tiles, tile_start_out);
+                                                    c->inst_tile, c->inst_idx, c->table_d, c->table_d_stride, ctr);
 }
 
 }  // namespace gs

@@ -57,7 +57,7 @@ __device__ __forceinline__ uint32_t to_u8(float v) {
 }
 
 __global__ void __launch_bounds__(256) k_raster(const float4 *__restrict__ inst_rec,
-                                                const uint32_t *__restrict__ tile_start,
+                                                const uint2 *__restrict__ tile_range,
                                                 const FrameParams *__restrict__ fp) {
   const RenderConsts &rc = fp->rc;
   void *out = fp->out;
@@ -76,7 +76,8 @@ __global__ void __launch_bounds__(256) k_raster(const float4 *__restrict__ inst_
   const bool inside = (x < rc.width) && (y < rc.height);
   const float fx = (float)x + 0.5f, fy = (float)y + 0.5f;  // pixel centre, GL window coordinates
 
-  const uint32_t start = tile_start[tile], end = tile_start[tile + 1];
+  const uint2 range = tile_range[tile];
+  const uint32_t start = range.x, end = range.y;
   const uint32_t count = end - start;
   const uint32_t n_chunks = (count + kChunk - 1) / kChunk;
 
@@ -188,8 +189,8 @@ __global__ void __launch_bounds__(256) k_assemble(const void *__restrict__ gathe
 }
 
 void launch_raster(gs_context *c, const FrameParams *fp, uint32_t n_tiles, const float4 *inst_rec,
-                   const uint32_t *tile_start, cudaStream_t stream) {
-  k_raster<<<n_tiles, 256, 0, stream>>>(inst_rec, tile_start, fp);
+                   const uint2 *tile_range, cudaStream_t stream) {
+  k_raster<<<n_tiles, 256, 0, stream>>>(inst_rec, tile_range, fp);
 }
 
 void launch_assemble(gs_context *c, const void *gathered, uint32_t tiles_per_rank, uint32_t world, uint32_t width,

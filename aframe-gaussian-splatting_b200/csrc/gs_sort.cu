@@ -8,6 +8,8 @@
 //
 // Bit-exactness: JS evaluates in fp64 with IEEE rounding after every operation; the kernels use
 // __dmul_rn/__dadd_rn so nothing is contracted, and ToInt32 is restated exactly (js_to_int32).
+#include <type_traits>
+
 #include "gs_common.cuh"
 
 namespace gs {
@@ -135,7 +137,8 @@ struct RadixArgs {
   // tile passes
   const uint16_t *inst_tile;
   const uint32_t *inst_idx;
-  uint8_t *inst_dig_b;
+  uint16_t *inst_tile_b;  // T1 output / T2 input: full tile id
+  uint16_t *inst_tile_f;  // T2 output: tile id in final order
   uint32_t *inst_idx_b;
   const float4 *proj_rec;
   float4 *inst_rec;
@@ -169,9 +172,11 @@ __device__ __forceinline__ void load_elem(const RadixArgs &a, uint32_t i, const 
     pay = a.idx_a[i];
   } else if (PASS == PASS_T1) {
     const uint16_t t = a.inst_tile[i];
-    if (t != kNoTile) { digit = t & 255; hi = (uint32_t)t >> 8; pay = a.inst_idx[i]; }
+    if (t != kNoTile) { digit = t & 255; hi = t; pay = a.inst_idx[i]; }
   } else {
-    digit = a.inst_dig_b[i];
+    const uint16_t t = a.inst_tile_b[i];
+    digit = (uint32_t)t >> 8;
+    hi = t;
     pay = a.inst_idx_b[i];
   }
 }
@@ -232,7 +237,9 @@ __global__ void __launch_bounds__(256) k_radix_scan(RadixArgs a) {
   __shared__ uint32_t s_carry;
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t n = pass_n<PASS>(a);
-  const uint32_t num_chunks = (n + kRadixTile - 1) / kRadixTile;
+  // T1's histograms come from k_emit, one column per 2048-instance window (two per 4096-element chunk)
+  const uint32_t col_elems = (PASS == PASS_T1) ? (uint32_t)kRadixTile / 2 : (uint32_t)kRadixTile;
+  const uint32_t num_chunks = (n + col_elems - 1) / col_elems;
   uint32_t *row = a.table + (size_t)blockIdx.x * a.stride;
   if (tid == 0) s_carry = 0;
   __syncthreads();
@@ -273,7 +280,9 @@ __global__ void __launch_bounds__(kScatThreads, 2) k_radix_scatter(RadixArgs a) 
   __shared__ uint32_t s_loc[256];     // slot of the digit's first element in the staged (locally sorted) chunk
   __shared__ uint32_t s_warp_tot[8];
   __shared__ uint32_t s_pay[kRadixTile];
-  __shared__ uint8_t s_hi[kRadixTile];
+  // value carried to the next pass: D1 -> high key byte, T1/T2 -> the 16-bit tile id
+  using hi_t = typename std::conditional<(PASS == PASS_T1 || PASS == PASS_T2), uint16_t, uint8_t>::type;
+  __shared__ hi_t s_hi[(PASS == PASS_D2) ? 1 : kRadixTile];
   __shared__ uint8_t s_dig[kRadixTile];
   __shared__ uint32_t s_total;
   FrameCounters *ctr = a.ctr;
@@ -304,12 +313,12 @@ __global__ void __launch_bounds__(kScatThreads, 2) k_radix_scatter(RadixArgs a) 
 
   for (uint32_t c = blockIdx.x; c < num_chunks; c += gridDim.x) {
     // this chunk's per-digit offset: issued first so its latency hides behind the ranking
-    const uint32_t toff = tid < 256 ? __ldg(a.table + (size_t)tid * a.stride + c) : 0u;
+    const uint32_t toff = tid < 256 ? __ldg(a.table + (size_t)tid * a.stride + (PASS == PASS_T1 ? 2 * c : c)) : 0u;
     for (uint32_t k = tid; k < kScatWarps * 256; k += kScatThreads) (&wcnt[0][0])[k] = 0u;
     // ---- load (warp-striped: consecutive lanes read consecutive elements) ----
     const uint32_t base = c * kRadixTile + warp * (32 * kScatItems) + lane;
     uint32_t digit[kScatItems], pay[kScatItems], rank[kScatItems];
-    uint8_t hi[kScatItems];
+    hi_t hi[kScatItems];
     uint32_t dummy = 0;
 #pragma unroll
     for (int s = 0; s < kScatItems; ++s) {
@@ -320,7 +329,7 @@ __global__ void __launch_bounds__(kScatThreads, 2) k_radix_scatter(RadixArgs a) 
       if (i < n) {
         uint32_t h8;
         load_elem<PASS>(a, i, dr, digit[s], pay[s], h8, dummy);
-        hi[s] = (uint8_t)h8;
+        hi[s] = (hi_t)h8;
       }
     }
     __syncthreads();
@@ -363,7 +372,7 @@ __global__ void __launch_bounds__(kScatThreads, 2) k_radix_scatter(RadixArgs a) 
       const uint32_t lp = s_loc[d] + wcnt[warp][d] + rank[s];
       s_pay[lp] = pay[s];
       s_dig[lp] = (uint8_t)d;
-      if (PASS == PASS_D1 || PASS == PASS_T1) s_hi[lp] = hi[s];
+      if (PASS != PASS_D2) s_hi[lp] = hi[s];
     }
     __syncthreads();
     // ---- write out: consecutive threads write consecutive slots of the same digit run (coalesced) ----
@@ -378,15 +387,28 @@ __global__ void __launch_bounds__(kScatThreads, 2) k_radix_scatter(RadixArgs a) 
         a.order[pos] = p;
       } else if (PASS == PASS_T1) {
         a.inst_idx_b[pos] = p;
-        a.inst_dig_b[pos] = s_hi[i];
+        a.inst_tile_b[pos] = s_hi[i];
       } else {
         const float4 r0 = __ldg(a.proj_rec + 2 * (size_t)p);
         const float4 r1 = __ldg(a.proj_rec + 2 * (size_t)p + 1);
         a.inst_rec[2 * (size_t)pos] = r0;
         a.inst_rec[2 * (size_t)pos + 1] = r1;
+        a.inst_tile_f[pos] = s_hi[i];
       }
     }
     __syncthreads();
+  }
+}
+
+// {start, end} of every tile's run in the final (tile, draw order) instance array; tiles without instances keep
+// the {0, 0} the per-frame memset wrote.  One thread per instance, neighbours compared.
+__global__ void __launch_bounds__(256) k_tile_ranges(const uint16_t *__restrict__ tile_f, FrameCounters *ctr,
+                                                     uint2 *__restrict__ range) {
+  const uint32_t n = ctr->overflow ? 0u : ctr->n_inst_kept;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const uint32_t t = tile_f[i];
+    if (i == 0 || tile_f[i - 1] != t) range[t].x = i;
+    if (i == n - 1 || tile_f[i + 1] != t) range[t].y = i + 1;
   }
 }
 
@@ -412,7 +434,8 @@ static RadixArgs make_args(gs_context *c, FrameCounters *ctr) {
   a.order = c->order;
   a.inst_tile = c->inst_tile;
   a.inst_idx = c->inst_idx;
-  a.inst_dig_b = c->inst_dig_b;
+  a.inst_tile_b = c->inst_tile_b;
+  a.inst_tile_f = c->inst_tile_f;
   a.inst_idx_b = c->inst_idx_b;
   a.proj_rec = c->proj_rec;
   a.inst_rec = nullptr;
@@ -422,7 +445,7 @@ static RadixArgs make_args(gs_context *c, FrameCounters *ctr) {
 template <int PASS>
 static void run_pass(gs_context *c, RadixArgs &a, uint64_t n_max) {
   const int grid = persistent_grid(c, n_max, kRadixTile, 8);
-  k_radix_hist<PASS><<<grid, kRadixThreads, 0, c->stream>>>(a);
+  if (PASS != PASS_T1) k_radix_hist<PASS><<<grid, kRadixThreads, 0, c->stream>>>(a);
   k_radix_scan<PASS><<<256, 256, 0, c->stream>>>(a);
   k_radix_scatter<PASS><<<grid, kScatThreads, 0, c->stream>>>(a);
 }
@@ -437,7 +460,8 @@ void launch_depth_radix(gs_context *c, FrameCounters *ctr) {
   run_pass<PASS_D2>(c, a, c->n);
 }
 
-// stable sort of the tile instances by tile id (6 launches); T2 writes the per-tile record lists
+// stable sort of the tile instances by tile id (5 launches: T1's histogram is produced by k_emit);
+// T2 writes the per-tile record lists
 void launch_tile_radix(gs_context *c, FrameCounters *ctr, float4 *inst_rec_out) {
   RadixArgs a = make_args(c, ctr);
   a.inst_rec = inst_rec_out;
@@ -446,6 +470,11 @@ void launch_tile_radix(gs_context *c, FrameCounters *ctr, float4 *inst_rec_out) 
   a.stride = c->table_d_stride;
   run_pass<PASS_T1>(c, a, c->cap_inst);
   run_pass<PASS_T2>(c, a, c->cap_inst);
+}
+
+void launch_tile_ranges(gs_context *c, FrameCounters *ctr, uint2 *tile_range_out) {
+  const int grid = persistent_grid(c, c->cap_inst, 256 * 8, 8);
+  k_tile_ranges<<<grid, 256, 0, c->stream>>>(c->inst_tile_f, ctr, tile_range_out);
 }
 
 }  // namespace gs
