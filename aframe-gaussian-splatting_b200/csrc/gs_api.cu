@@ -79,16 +79,18 @@ static int ensure_table(gs_context *c, uint64_t need) {
 
 static int ensure_scratch(gs_context *c) {
   if (c->scratch_cap >= c->cap && c->depth) return GS_OK;
-  dev_free(c->depth); dev_free(c->idx_a); dev_free(c->dig_a); dev_free(c->order);
-  dev_free(c->proj_rec); dev_free(c->rect); dev_free(c->table_n); dev_free(c->tile_total);
+  dev_free(c->depth); dev_free(c->idx_a); dev_free(c->dig_a); dev_free(c->table_n); dev_free(c->tile_total);
+  for (int i = 0; i < 2; ++i) { dev_free(c->order[i]); dev_free(c->proj_rec[i]); dev_free(c->rect[i]); }
   dev_free(c->slice_prefix); dev_free(c->ent); dev_free(c->ent_off);
   const size_t n = c->cap;
   GS_CUDA(c, dev_alloc(&c->depth, n));
   GS_CUDA(c, dev_alloc(&c->idx_a, n));
   GS_CUDA(c, dev_alloc(&c->dig_a, n));
-  GS_CUDA(c, dev_alloc(&c->order, n));
-  GS_CUDA(c, dev_alloc(&c->proj_rec, 2 * n));
-  GS_CUDA(c, dev_alloc(&c->rect, n));
+  for (int i = 0; i < 2; ++i) {
+    GS_CUDA(c, dev_alloc(&c->order[i], n));
+    GS_CUDA(c, dev_alloc(&c->proj_rec[i], 2 * n));
+    GS_CUDA(c, dev_alloc(&c->rect[i], n));
+  }
   c->table_n_stride = (uint32_t)((n + kRadixTile - 1) / kRadixTile + 1);
   GS_CUDA(c, dev_alloc(&c->table_n, (size_t)256 * c->table_n_stride));
   GS_CUDA(c, dev_alloc(&c->tile_total, (n + kEmitTile - 1) / kEmitTile + 1));
@@ -138,11 +140,11 @@ static int ensure_frame(gs_context *c, gs_context::Slot &sl, size_t bytes) {
 }
 
 static void drop_graphs(gs_context *c) {
-  for (auto &sl : c->slot) {
-    for (auto &g : sl.graph)
-      if (g) { cudaGraphExecDestroy(g); g = nullptr; }
-    if (sl.graph_r) { cudaGraphExecDestroy(sl.graph_r); sl.graph_r = nullptr; }
-  }
+  auto kill = [](cudaGraphExec_t &g) { if (g) { cudaGraphExecDestroy(g); g = nullptr; } };
+  for (auto &sl : c->slot)
+    for (int i = 0; i < 2; ++i) {
+      kill(sl.graph_a[i][0]); kill(sl.graph_a[i][1]); kill(sl.graph_b[i]); kill(sl.graph_r[i]);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -189,10 +191,10 @@ extern "C" int gs_create(int device_ordinal, gs_context **out_ctx) {
   int prio_least = 0, prio_greatest = 0;
   cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest);
   if ((e = cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio_greatest)) != cudaSuccess) return bail("cudaStreamCreate", e);
+  if ((e = cudaStreamCreateWithPriority(&c->bstream, cudaStreamNonBlocking, prio_greatest)) != cudaSuccess) return bail("cudaStreamCreate", e);
   if ((e = cudaStreamCreateWithPriority(&c->rstream, cudaStreamNonBlocking, prio_least)) != cudaSuccess) return bail("cudaStreamCreate", e);
   if ((e = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
-  c->slot[0].index = 0;
-  c->slot[1].index = 1;
+  for (int i = 0; i < 3; ++i) c->slot[i].index = i;
   if ((e = cudaStreamCreateWithPriority(&c->aux_stream, cudaStreamNonBlocking, prio_greatest)) != cudaSuccess) return bail("cudaStreamCreate", e);
   for (int i = 0; i < 2; ++i) {
     if ((e = cudaEventCreateWithFlags(&c->ev_fork[i], cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
@@ -207,6 +209,7 @@ extern "C" int gs_create(int device_ordinal, gs_context **out_ctx) {
       if ((e = cudaEventCreate(&ev)) != cudaSuccess) return bail("cudaEventCreate", e);
     if ((e = cudaEventCreateWithFlags(&sl.ev_done, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
     if ((e = cudaEventCreateWithFlags(&sl.ev_binned, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
+    if ((e = cudaEventCreateWithFlags(&sl.ev_sorted, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
     if ((e = cudaEventCreate(&sl.ev_r0)) != cudaSuccess) return bail("cudaEventCreate", e);
     if ((e = cudaEventCreateWithFlags(&sl.ev_copied, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
     if ((e = cudaMalloc((void **)&sl.ctr, sizeof(FrameCounters))) != cudaSuccess) return bail("cudaMalloc", e);
@@ -237,9 +240,11 @@ extern "C" int gs_destroy(gs_context *c) {
   if (!c) return GS_OK;
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
+  if (c->bstream) cudaStreamSynchronize(c->bstream);
   if (c->rstream) cudaStreamSynchronize(c->rstream);
   dev_free(c->center_scale); dev_free(c->cov_color); dev_free(c->size_alpha);
-  dev_free(c->depth); dev_free(c->idx_a); dev_free(c->dig_a); dev_free(c->order); dev_free(c->proj_rec); dev_free(c->rect);
+  dev_free(c->depth); dev_free(c->idx_a); dev_free(c->dig_a);
+  for (int i = 0; i < 2; ++i) { dev_free(c->order[i]); dev_free(c->proj_rec[i]); dev_free(c->rect[i]); }
   dev_free(c->inst_tile); dev_free(c->inst_idx); dev_free(c->inst_tile_b); dev_free(c->inst_tile_f); dev_free(c->inst_idx_b);
   dev_free(c->inst_rec[0]); dev_free(c->inst_rec[1]);
   dev_free(c->tile_range[0]); dev_free(c->tile_range[1]); dev_free(c->quirk_table);
@@ -256,6 +261,7 @@ extern "C" int gs_destroy(gs_context *c) {
     for (auto &ev : sl.evp) if (ev) cudaEventDestroy(ev);
     if (sl.ev_done) cudaEventDestroy(sl.ev_done);
     if (sl.ev_binned) cudaEventDestroy(sl.ev_binned);
+    if (sl.ev_sorted) cudaEventDestroy(sl.ev_sorted);
     if (sl.ev_r0) cudaEventDestroy(sl.ev_r0);
     if (sl.ev_copied) cudaEventDestroy(sl.ev_copied);
   }
@@ -267,6 +273,7 @@ extern "C" int gs_destroy(gs_context *c) {
   }
   if (c->aux_stream) cudaStreamDestroy(c->aux_stream);
   if (c->rstream) cudaStreamDestroy(c->rstream);
+  if (c->bstream) cudaStreamDestroy(c->bstream);
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
@@ -381,14 +388,18 @@ extern "C" int gs_sort(gs_context *c, const float view[4], const float *cutout16
   int rc = drain(c);
   if (rc) return rc;
   if ((rc = ensure_scratch(c))) return rc;
+  GS_CUDA(c, cudaStreamSynchronize(c->bstream));
+  GS_CUDA(c, cudaStreamSynchronize(c->rstream));
   gs_context::Slot &sl = c->slot[0];
+  c->last_set = 0;
+  const FrameBufs bufs{c->order[0], c->proj_rec[0], c->rect[0], c->inst_rec[0], c->tile_range[0]};
   memset(sl.fp_host, 0, sizeof(FrameParams));
   fill_sort_consts(sl.fp_host->sc, view, cutout16_or_null);
   GS_CUDA(c, cudaMemcpyAsync(sl.fp, sl.fp_host, sizeof(FrameParams), cudaMemcpyHostToDevice, c->stream));
   GS_CUDA(c, cudaMemsetAsync(sl.ctr, 0, sizeof(FrameCounters), c->stream));
   GS_CUDA(c, cudaEventRecord(c->ev[0], c->stream));
-  launch_depth_cull(c, sl.fp, sl.ctr);
-  launch_depth_radix(c, sl.ctr);
+  launch_depth_cull(c, sl.fp, sl.ctr, c->stream);
+  launch_depth_radix(c, sl.ctr, bufs, c->stream);
   GS_CUDA(c, cudaGetLastError());
   GS_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
   GS_CUDA(c, cudaMemcpyAsync(c->sort_hdr, sl.ctr, sizeof(SortHeader), cudaMemcpyDeviceToDevice, c->stream));
@@ -405,7 +416,7 @@ extern "C" int gs_sort(gs_context *c, const float view[4], const float *cutout16
   c->order_count = sl.ctr_host->n_valid;
   if (out_count) *out_count = c->order_count;
   if (out_idx && c->order_count)
-    GS_CUDA(c, cudaMemcpy(out_idx, c->order, sizeof(uint32_t) * (size_t)c->order_count, cudaMemcpyDeviceToHost));
+    GS_CUDA(c, cudaMemcpy(out_idx, c->order[c->last_set], sizeof(uint32_t) * (size_t)c->order_count, cudaMemcpyDeviceToHost));
   return GS_OK;
 }
 
@@ -426,58 +437,68 @@ extern "C" uint32_t gs_owned_tiles(uint32_t width, uint32_t height, uint32_t ran
 
 // Everything one frame does on the main stream; all per-frame inputs come from sl.fp (device memory), so the same
 // sequence can be captured once into a CUDA graph and replayed.
-// The part of a frame that runs on the main stream: sort, projection, binning.  All per-frame inputs come from
-// sl.fp (device memory), so the sequence is captured once into a CUDA graph and replayed.
-static cudaError_t enqueue_main(gs_context *c, gs_context::Slot &sl, bool reuse, uint32_t n_tiles, bool external_events) {
+static FrameBufs slot_bufs(gs_context *c, const gs_context::Slot &sl) {
+  return FrameBufs{c->order[sl.set], c->proj_rec[sl.set], c->rect[sl.set], c->inst_rec[sl.set], c->tile_range[sl.set]};
+}
+
+// Stage A of a frame (sort stream): per-frame inputs to the device, depth sort, vertex shader.  All per-frame
+// inputs come from sl.fp (device memory), so each stage is captured once into a CUDA graph and replayed.
+static cudaError_t enqueue_sort_stage(gs_context *c, gs_context::Slot &sl, bool reuse, bool external_events) {
   auto rec = [&](cudaEvent_t ev, cudaStream_t st) {
     return external_events ? cudaEventRecordWithFlags(ev, st, cudaEventRecordExternal) : cudaEventRecord(ev, st);
   };
   cudaStream_t m = c->stream, x = c->aux_stream;
+  const FrameBufs b = slot_bufs(c, sl);
   cudaError_t e;
   if ((e = cudaMemcpyAsync(sl.fp, sl.fp_host, sizeof(FrameParams), cudaMemcpyHostToDevice, m))) return e;
   if ((e = cudaMemsetAsync(sl.ctr, 0, sizeof(FrameCounters), m))) return e;
-  if ((e = cudaMemsetAsync(c->tile_range[sl.index], 0, sizeof(uint2) * (size_t)n_tiles, m))) return e;
   if ((e = rec(sl.ev[0], m))) return e;
-  uint32_t launches = 0;
   if (reuse) {
     if ((e = cudaMemcpyAsync(sl.ctr, c->sort_hdr, sizeof(SortHeader), cudaMemcpyDeviceToDevice, m))) return e;
   } else {
-    launch_depth_cull(c, sl.fp, sl.ctr);
-    launches += 1;
+    launch_depth_cull(c, sl.fp, sl.ctr, m);
   }
-  // fork 1: the vertex-shader kernel only needs the cull result, so it runs beside the depth radix passes
+  // fork: the vertex-shader kernel only needs the cull result, so it runs beside the depth radix passes
   if ((e = cudaEventRecord(c->ev_fork[0], m))) return e;
   if ((e = cudaStreamWaitEvent(x, c->ev_fork[0], 0))) return e;
   if ((e = rec(sl.evp[0], x))) return e;
-  launch_project(c, sl.fp, x);
+  launch_project(c, sl.fp, b, x);
   if ((e = rec(sl.evp[1], x))) return e;
   if ((e = cudaEventRecord(c->ev_join[0], x))) return e;
   if (!reuse) {
-    launch_depth_radix(c, sl.ctr);
-    launches += 6;
+    launch_depth_radix(c, sl.ctr, b, m);
     if ((e = cudaMemcpyAsync(c->sort_hdr, sl.ctr, sizeof(SortHeader), cudaMemcpyDeviceToDevice, m))) return e;
   }
   if ((e = rec(sl.ev[1], m))) return e;
   if ((e = cudaStreamWaitEvent(m, c->ev_join[0], 0))) return e;
-  if ((e = rec(sl.ev[2], m))) return e;
-  launch_emit(c, sl.fp, sl.ctr);                          // 2 launches (k_emit also histograms pass T1)
-  launch_tile_radix(c, sl.ctr, c->inst_rec[sl.index]);   // 5 launches
-  launch_tile_ranges(c, sl.ctr, c->tile_range[sl.index]);
-  if ((e = rec(sl.ev[3], m))) return e;
-  launches += 9;
-  sl.launches = launches + 1;
   return cudaGetLastError();
 }
 
-// The raster of a frame, on the raster stream: it only reads this slot's inst_rec / tile_start, so the next
-// frame's sort + binning (main stream, other slot) runs underneath it.
-static cudaError_t enqueue_raster(gs_context *c, gs_context::Slot &sl, uint32_t n_tiles, bool external_events) {
+// Stage B (bin stream): tile instances in draw order, stable sort by tile, per-tile record lists and ranges.
+static cudaError_t enqueue_bin_stage(gs_context *c, gs_context::Slot &sl, uint32_t n_tiles, bool external_events) {
+  auto rec = [&](cudaEvent_t ev, cudaStream_t st) {
+    return external_events ? cudaEventRecordWithFlags(ev, st, cudaEventRecordExternal) : cudaEventRecord(ev, st);
+  };
+  cudaStream_t m = c->bstream;
+  const FrameBufs b = slot_bufs(c, sl);
+  cudaError_t e;
+  if ((e = cudaMemsetAsync(b.tile_range, 0, sizeof(uint2) * (size_t)n_tiles, m))) return e;
+  if ((e = rec(sl.ev[2], m))) return e;
+  launch_emit(c, sl.fp, sl.ctr, b, m);   // 2 launches (k_emit also histograms pass T1)
+  launch_tile_radix(c, sl.ctr, b, m);    // 5 launches
+  launch_tile_ranges(c, sl.ctr, b, m);
+  if ((e = rec(sl.ev[3], m))) return e;
+  return cudaGetLastError();
+}
+
+// Stage C (raster stream, low priority): reads only this frame's inst_rec / tile_range copy.
+static cudaError_t enqueue_raster_stage(gs_context *c, gs_context::Slot &sl, uint32_t n_tiles, bool external_events) {
   auto rec = [&](cudaEvent_t ev, cudaStream_t st) {
     return external_events ? cudaEventRecordWithFlags(ev, st, cudaEventRecordExternal) : cudaEventRecord(ev, st);
   };
   cudaError_t e;
   if ((e = rec(sl.ev_r0, c->rstream))) return e;
-  launch_raster(c, sl.fp, n_tiles, c->inst_rec[sl.index], c->tile_range[sl.index], c->rstream);
+  launch_raster(c, sl.fp, n_tiles, slot_bufs(c, sl), c->rstream);
   if ((e = rec(sl.ev[4], c->rstream))) return e;
   return cudaGetLastError();
 }
@@ -509,6 +530,9 @@ static int run_graph(gs_context *c, cudaGraphExec_t &ge, cudaStream_t stream, F 
   return GS_OK;
 }
 
+// Three frames overlap: while frame k is rasterised (stream C), frame k+1 is binned (stream B) and frame k+2 is
+// sorted / projected (stream A).  A and B are high priority: their short latency-bound kernels slot in as the
+// long issue-bound raster's CTAs retire.  Stage hand-offs are events; buffers between stages are double-buffered.
 static int launch_frame(gs_context *c, gs_context::Slot &sl, bool reuse, uint32_t n_tiles) {
   // (re)capture when anything baked into the launches changed
   gs_context::GraphKey k;
@@ -517,19 +541,30 @@ static int launch_frame(gs_context *c, gs_context::Slot &sl, bool reuse, uint32_
     drop_graphs(c);
     c->gkey = k;
   }
-  // this slot's previous raster (two frames ago) must have finished reading inst_rec / tile_start / fp
-  GS_CUDA(c, cudaStreamWaitEvent(c->stream, sl.ev_done, 0));
-  int rc = run_graph(c, sl.graph[reuse ? 1 : 0], c->stream, [&](bool ext) { return enqueue_main(c, sl, reuse, n_tiles, ext); });
+  const int set = sl.set;
+  // A: order/proj_rec/rect[set] must no longer be read by the binning stage that used them last
+  if (c->sort_set_free[set]) GS_CUDA(c, cudaStreamWaitEvent(c->stream, c->sort_set_free[set], 0));
+  int rc = run_graph(c, sl.graph_a[set][reuse ? 1 : 0], c->stream, [&](bool ext) { return enqueue_sort_stage(c, sl, reuse, ext); });
   if (rc) return rc;
-  GS_CUDA(c, cudaEventRecord(sl.ev_binned, c->stream));
+  GS_CUDA(c, cudaEventRecord(sl.ev_sorted, c->stream));
+  // B: needs A of this frame; inst_rec/tile_range[set] must no longer be read by the raster that used them last
+  GS_CUDA(c, cudaStreamWaitEvent(c->bstream, sl.ev_sorted, 0));
+  if (c->bin_set_free[set]) GS_CUDA(c, cudaStreamWaitEvent(c->bstream, c->bin_set_free[set], 0));
+  if ((rc = run_graph(c, sl.graph_b[set], c->bstream, [&](bool ext) { return enqueue_bin_stage(c, sl, n_tiles, ext); }))) return rc;
+  GS_CUDA(c, cudaEventRecord(sl.ev_binned, c->bstream));
+  c->sort_set_free[set] = sl.ev_binned;
+  // C
   GS_CUDA(c, cudaStreamWaitEvent(c->rstream, sl.ev_binned, 0));
-  return run_graph(c, sl.graph_r, c->rstream, [&](bool ext) { return enqueue_raster(c, sl, n_tiles, ext); });
+  if ((rc = run_graph(c, sl.graph_r[set], c->rstream, [&](bool ext) { return enqueue_raster_stage(c, sl, n_tiles, ext); }))) return rc;
+  sl.launches = (reuse ? 0u : 7u) + 1u + 8u + 1u;
+  return GS_OK;
 }
 
 // after the frame's kernels: counters (and the frame, when the caller's buffer is host memory) go to the host on
 // the copy stream, so the next frame's kernels overlap the PCIe transfer
 static int enqueue_readback(gs_context *c, gs_context::Slot &sl) {
   GS_CUDA(c, cudaEventRecord(sl.ev_done, c->rstream));
+  c->bin_set_free[sl.set] = sl.ev_done;
   GS_CUDA(c, cudaStreamWaitEvent(c->copy_stream, sl.ev_done, 0));
   GS_CUDA(c, cudaMemcpyAsync(sl.ctr_host, sl.ctr, sizeof(FrameCounters), cudaMemcpyDeviceToHost, c->copy_stream));
   if (sl.host_out)
@@ -575,8 +610,12 @@ static int submit(gs_context *c, gs_context::Slot &sl) {
     fp.out = sl.out_user;
   }
   const bool reuse = (p->flags & GS_RENDER_REUSE_SORT) && c->have_order;
+  // a frame normally takes the buffer set the previous frame did not; a frame that reuses the last sort must read
+  // that sort's set, so it runs in it
+  sl.set = reuse ? c->last_set : (c->last_set ^ 1);
   if ((rcode = launch_frame(c, sl, reuse, rc.n_tiles))) return rcode;
   if ((rcode = enqueue_readback(c, sl))) return rcode;
+  c->last_set = sl.set;
   sl.pending = true;
   c->have_order = true;
   return GS_OK;
@@ -591,7 +630,8 @@ static int wait_slot(gs_context *c, gs_context::Slot &sl, gs_stats *stats) {
     if (attempt == 7) return fail(c, GS_ERR_CAPACITY, "instance buffer kept overflowing");
     // instance buffer too small: grow to the measured demand and run this frame again
     const uint64_t need = std::max<uint64_t>(sl.ctr_host->n_inst + sl.ctr_host->n_inst / 8, c->cap_inst * 2);
-    GS_CUDA(c, cudaStreamSynchronize(c->stream));  // the other slot's frame may still be using the buffers
+    GS_CUDA(c, cudaStreamSynchronize(c->stream));  // the other slots' frames may still be using the buffers
+    GS_CUDA(c, cudaStreamSynchronize(c->bstream));
     GS_CUDA(c, cudaStreamSynchronize(c->rstream));
     int rcode = ensure_instances(c, need);
     if (rcode) return rcode;
@@ -605,7 +645,7 @@ static int wait_slot(gs_context *c, gs_context::Slot &sl, gs_stats *stats) {
   c->stats.height = sl.params.height;
   cudaEventElapsedTime(&c->stats.ms_sort, sl.ev[0], sl.ev[1]);
   cudaEventElapsedTime(&c->stats.ms_project, sl.evp[0], sl.evp[1]);  // on the aux stream, overlapping the sort
-  cudaEventElapsedTime(&c->stats.ms_bin, sl.ev[2], sl.ev[3]);
+  cudaEventElapsedTime(&c->stats.ms_bin, sl.ev[2], sl.ev[3]);  // on the bin stream
   cudaEventElapsedTime(&c->stats.ms_raster, sl.ev_r0, sl.ev[4]);
   cudaEventElapsedTime(&c->stats.ms_total, sl.ev[0], sl.ev[4]);
   c->order_count = sl.ctr_host->n_valid;
@@ -623,14 +663,16 @@ extern "C" int gs_render_async(gs_context *c, const gs_render_params *p, void *o
   if (n_tiles >= 0xFFFFu) return fail(c, GS_ERR_INVALID, "more than 65534 tiles");
   GS_CUDA(c, cudaSetDevice(c->device));
   const uint64_t ticket = c->next_ticket;
-  gs_context::Slot &sl = c->slot[ticket & 1];
+  gs_context::Slot &sl = c->slot[ticket % 3];
   int rcode;
   if (sl.pending && (rcode = wait_slot(c, sl, nullptr))) return rcode;  // slot reuse: its previous frame must be done
+  if ((p->flags & GS_RENDER_REUSE_SORT) && c->have_order && (rcode = drain(c))) return rcode;  // runs in the last sort's buffers
   // growing any shared buffer needs an idle pipeline
   const bool grow = !(c->scratch_cap >= c->cap && c->depth) || !(n_tiles <= c->tiles_cap && c->tile_range[0]) || c->cap_inst == 0;
   if (grow) {
     if ((rcode = drain(c))) return rcode;
     GS_CUDA(c, cudaStreamSynchronize(c->stream));
+    GS_CUDA(c, cudaStreamSynchronize(c->bstream));
     GS_CUDA(c, cudaStreamSynchronize(c->rstream));
     if ((rcode = ensure_scratch(c))) return rcode;
     if ((rcode = ensure_tiles(c, n_tiles))) return rcode;
@@ -648,8 +690,8 @@ extern "C" int gs_wait(gs_context *c, uint64_t ticket, gs_stats *stats) {
   if (!c) return GS_ERR_INVALID;
   if (ticket >= c->next_ticket) return fail(c, GS_ERR_INVALID, "gs_wait: unknown ticket");
   GS_CUDA(c, cudaSetDevice(c->device));
-  gs_context::Slot &sl = c->slot[ticket & 1];
-  if (ticket + 2 < c->next_ticket || !sl.pending) {  // already completed (e.g. by a slot-reuse wait): stats of that frame are gone, frame is in place
+  gs_context::Slot &sl = c->slot[ticket % 3];
+  if (ticket + 3 < c->next_ticket || !sl.pending) {  // already completed (e.g. by a slot-reuse wait): stats of that frame are gone, frame is in place
     if (stats) *stats = c->stats;
     return GS_OK;
   }
@@ -670,12 +712,12 @@ extern "C" int gs_get_stats(const gs_context *c, gs_stats *out) {
 }
 
 extern "C" int gs_read_projected(gs_context *c, uint32_t first, uint32_t n, float *out8) {
-  if (!c || !out8 || (uint64_t)first + n > c->n || !c->proj_rec) return GS_ERR_INVALID;
+  if (!c || !out8 || (uint64_t)first + n > c->n || !c->proj_rec[0]) return GS_ERR_INVALID;
   GS_CUDA(c, cudaSetDevice(c->device));
   std::vector<float> rec((size_t)n * 8);
   std::vector<uint32_t> rect(n);
-  GS_CUDA(c, cudaMemcpy(rec.data(), c->proj_rec + 2 * (size_t)first, sizeof(float) * 8 * (size_t)n, cudaMemcpyDeviceToHost));
-  GS_CUDA(c, cudaMemcpy(rect.data(), c->rect + first, sizeof(uint32_t) * (size_t)n, cudaMemcpyDeviceToHost));
+  GS_CUDA(c, cudaMemcpy(rec.data(), c->proj_rec[c->last_set] + 2 * (size_t)first, sizeof(float) * 8 * (size_t)n, cudaMemcpyDeviceToHost));
+  GS_CUDA(c, cudaMemcpy(rect.data(), c->rect[c->last_set] + first, sizeof(uint32_t) * (size_t)n, cudaMemcpyDeviceToHost));
   for (uint32_t i = 0; i < n; ++i) {
     memcpy(out8 + 8 * (size_t)i, rec.data() + 8 * (size_t)i, 32);
     memcpy(out8 + 8 * (size_t)i + 7, &rect[i], 4);
@@ -734,6 +776,7 @@ extern "C" int gs_synchronize(gs_context *c) {
   if (!c) return GS_ERR_INVALID;
   GS_CUDA(c, cudaSetDevice(c->device));
   GS_CUDA(c, cudaStreamSynchronize(c->stream));
+  GS_CUDA(c, cudaStreamSynchronize(c->bstream));
   GS_CUDA(c, cudaStreamSynchronize(c->rstream));
   return GS_OK;
 }

@@ -103,9 +103,11 @@ struct gs_context {
   float *depth = nullptr;        // f32 depth or GS_DEPTH_REJECT
   uint32_t *idx_a = nullptr;     // after depth pass 1
   uint8_t *dig_a = nullptr;
-  uint32_t *order = nullptr;     // draw order (== reference sortedIndexes)
-  float4 *proj_rec = nullptr;    // 2 x float4 per splat
-  uint32_t *rect = nullptr;      // packed tile rect per splat
+  // outputs of the sort/project stage, consumed by the binning stage of the same frame: double-buffered so that
+  // frame k+1 is sorted while frame k is binned
+  uint32_t *order[2] = {nullptr, nullptr};    // draw order (== reference sortedIndexes)
+  float4 *proj_rec[2] = {nullptr, nullptr};   // 2 x float4 per splat
+  uint32_t *rect[2] = {nullptr, nullptr};     // packed tile rect per splat
   uint32_t *table_n = nullptr;   // radix chunk histograms of the depth passes [256][table_n_stride]
   uint32_t table_n_stride = 0;
   uint32_t *totals = nullptr;    // [512]: digit totals of the depth / tile passes
@@ -144,9 +146,12 @@ struct gs_context {
     cudaEvent_t ev[5]{};                     // stage boundaries (timing)
     cudaEvent_t evp[2]{};                    // k_project on the aux stream (timing)
     cudaEvent_t ev_done = nullptr, ev_copied = nullptr;
-    cudaGraphExec_t graph[2] = {nullptr, nullptr};  // sort+project+bin on the main stream, [reuse_sort]
-    cudaGraphExec_t graph_r = nullptr;              // raster on the raster stream
-    cudaEvent_t ev_binned = nullptr;                // main-stream part of this slot's frame finished
+    // CUDA graphs of the three stages, one per buffer set this slot can be paired with
+    cudaGraphExec_t graph_a[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};  // sort + project, [set][reuse_sort]
+    cudaGraphExec_t graph_b[2] = {nullptr, nullptr};                           // binning, [set]
+    cudaGraphExec_t graph_r[2] = {nullptr, nullptr};                           // raster, [set]
+    cudaEvent_t ev_sorted = nullptr;                // sort/project stage of this slot's frame finished
+    cudaEvent_t ev_binned = nullptr;                // binning stage finished
     cudaEvent_t ev_r0 = nullptr;                    // raster start (timing)
     int index = 0;
     bool pending = false;
@@ -155,8 +160,13 @@ struct gs_context {
     size_t out_bytes = 0;
     gs_render_params params{};
     uint32_t launches = 0;
-  } slot[2];
+    int set = 0;                                    // which order/proj_rec/rect and inst_rec/tile_range copy it uses
+  } slot[3];
   uint64_t next_ticket = 0;
+  cudaStream_t bstream = nullptr;                   // binning stage (high priority, like the sort stage's `stream`)
+  cudaEvent_t sort_set_free[2] = {nullptr, nullptr};  // last binning stage that read order/proj_rec/rect[i]
+  cudaEvent_t bin_set_free[2] = {nullptr, nullptr};   // last raster that read inst_rec/tile_range[i]
+  int last_set = 0;                                 // set holding the most recent sort (GS_RENDER_REUSE_SORT, read-backs)
   cudaStream_t rstream = nullptr;   // raster stream: frame k is rasterised here while frame k+1 is sorted / binned
   cudaStream_t copy_stream = nullptr;
   cudaStream_t aux_stream = nullptr;             // runs k_project beside the depth radix passes
@@ -174,16 +184,24 @@ struct gs_context {
 
 namespace gs {
 
+// buffers one frame's stages hand to each other (a pair of double-buffered sets)
+struct FrameBufs {
+  uint32_t *order;
+  float4 *proj_rec;
+  uint32_t *rect;
+  float4 *inst_rec;
+  uint2 *tile_range;
+};
+
 // -- launchers (each .cu file owns its kernels); every per-frame input comes from device memory (fp, ctr) --
-void launch_depth_cull(gs_context *c, const FrameParams *fp, FrameCounters *ctr);
-void launch_depth_radix(gs_context *c, FrameCounters *ctr);  // 6 launches -> c->order
+void launch_depth_cull(gs_context *c, const FrameParams *fp, FrameCounters *ctr, cudaStream_t st);
+void launch_depth_radix(gs_context *c, FrameCounters *ctr, const FrameBufs &b, cudaStream_t st);  // 6 launches -> b.order
 void launch_pack(gs_context *c, const uint8_t *rows_dev, uint32_t first, uint32_t n);
-void launch_project(gs_context *c, const FrameParams *fp, cudaStream_t stream);
-void launch_emit(gs_context *c, const FrameParams *fp, FrameCounters *ctr);  // 2 launches
-void launch_tile_radix(gs_context *c, FrameCounters *ctr, float4 *inst_rec_out);  // 5 launches (T1 histogram comes from k_emit)
-void launch_tile_ranges(gs_context *c, FrameCounters *ctr, uint2 *tile_range_out);
-void launch_raster(gs_context *c, const FrameParams *fp, uint32_t n_tiles, const float4 *inst_rec,
-                   const uint2 *tile_range, cudaStream_t stream);
+void launch_project(gs_context *c, const FrameParams *fp, const FrameBufs &b, cudaStream_t st);
+void launch_emit(gs_context *c, const FrameParams *fp, FrameCounters *ctr, const FrameBufs &b, cudaStream_t st);  // 2 launches
+void launch_tile_radix(gs_context *c, FrameCounters *ctr, const FrameBufs &b, cudaStream_t st);  // 5 launches
+void launch_tile_ranges(gs_context *c, FrameCounters *ctr, const FrameBufs &b, cudaStream_t st);
+void launch_raster(gs_context *c, const FrameParams *fp, uint32_t n_tiles, const FrameBufs &b, cudaStream_t st);
 void launch_assemble(gs_context *c, const void *gathered, uint32_t tiles_per_rank, uint32_t world, uint32_t width,
                      uint32_t height, int32_t format, void *out_frame);
 

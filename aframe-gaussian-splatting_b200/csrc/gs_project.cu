@@ -451,25 +451,25 @@ __global__ void __launch_bounds__(kEmitThreads, 4) k_emit(const uint2 *__restric
   }
 }
 
-void launch_project(gs_context *c, const FrameParams *fp, cudaStream_t stream) {
+void launch_project(gs_context *c, const FrameParams *fp, const FrameBufs &b, cudaStream_t stream) {
   uint64_t blocks = ((uint64_t)c->n + 255) / 256;
   const uint64_t cap = (uint64_t)c->sm_count * 16;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
-  k_project<<<(int)blocks, 256, 0, stream>>>(c->center_scale, c->cov_color, c->depth, c->n, fp, c->proj_rec, c->rect);
+  k_project<<<(int)blocks, 256, 0, stream>>>(c->center_scale, c->cov_color, c->depth, c->n, fp, b.proj_rec, b.rect);
 }
 
-void launch_emit(gs_context *c, const FrameParams *fp, FrameCounters *ctr) {
+void launch_emit(gs_context *c, const FrameParams *fp, FrameCounters *ctr, const FrameBufs &b, cudaStream_t st) {
   uint64_t tiles = ((uint64_t)c->n + kEmitTile - 1) / kEmitTile;
   const uint64_t cap = (uint64_t)c->sm_count * 8;
   if (tiles > cap) tiles = cap;
   if (tiles < 1) tiles = 1;
-  k_count<<<(int)tiles, kEmitThreads, 0, c->stream>>>(c->order, c->rect, c->ent, c->ent_off, c->tile_total,
+  k_count<<<(int)tiles, kEmitThreads, 0, st>>>(b.order, b.rect, c->ent, c->ent_off, c->tile_total,
                                                       c->slice_prefix, ctr, fp);
   uint64_t wins = (c->cap_inst + kEmitWindow - 1) / kEmitWindow;
   if (wins > (uint64_t)c->sm_count * 4) wins = (uint64_t)c->sm_count * 4;
   if (wins < 1) wins = 1;
-  k_emit<<<(int)wins, kEmitThreads, 0, c->stream>>>(c->ent, c->ent_off, c->slice_prefix, c->proj_rec, fp, c->cap_inst,
+  k_emit<<<(int)wins, kEmitThreads, 0, st>>>(c->ent, c->ent_off, c->slice_prefix, b.proj_rec, fp, c->cap_inst,
                                                     c->inst_tile, c->inst_idx, c->table_d, c->table_d_stride, ctr);
 }
 

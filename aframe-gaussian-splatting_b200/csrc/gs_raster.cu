@@ -188,9 +188,8 @@ __global__ void __launch_bounds__(256) k_assemble(const void *__restrict__ gathe
   else ((float4 *)out)[dst] = ((const float4 *)gathered)[src];
 }
 
-void launch_raster(gs_context *c, const FrameParams *fp, uint32_t n_tiles, const float4 *inst_rec,
-                   const uint2 *tile_range, cudaStream_t stream) {
-  k_raster<<<n_tiles, 256, 0, stream>>>(inst_rec, tile_range, fp);
+void launch_raster(gs_context *c, const FrameParams *fp, uint32_t n_tiles, const FrameBufs &b, cudaStream_t st) {
+  k_raster<<<n_tiles, 256, 0, st>>>(b.inst_rec, b.tile_range, fp);
 }
 
 void launch_assemble(gs_context *c, const void *gathered, uint32_t tiles_per_rank, uint32_t world, uint32_t width,

@@ -419,62 +419,61 @@ static int persistent_grid(gs_context *c, uint64_t n_elems, int per_cta, int cta
   return (int)(tiles < cap ? tiles : cap);
 }
 
-void launch_depth_cull(gs_context *c, const FrameParams *fp, FrameCounters *ctr) {
+void launch_depth_cull(gs_context *c, const FrameParams *fp, FrameCounters *ctr, cudaStream_t st) {
   const int grid = persistent_grid(c, c->n, 256 * 4, 8);
-  k_depth_cull<<<grid, 256, 0, c->stream>>>(c->center_scale, c->size_alpha, c->n, fp, c->depth, ctr);
+  k_depth_cull<<<grid, 256, 0, st>>>(c->center_scale, c->size_alpha, c->n, fp, c->depth, ctr);
 }
 
-static RadixArgs make_args(gs_context *c, FrameCounters *ctr) {
+static RadixArgs make_args(gs_context *c, FrameCounters *ctr, const FrameBufs &b) {
   RadixArgs a{};
   a.ctr = ctr;
   a.n_host = c->n;
   a.depth = c->depth;
   a.idx_a = c->idx_a;
   a.dig_a = c->dig_a;
-  a.order = c->order;
+  a.order = b.order;
   a.inst_tile = c->inst_tile;
   a.inst_idx = c->inst_idx;
   a.inst_tile_b = c->inst_tile_b;
   a.inst_tile_f = c->inst_tile_f;
   a.inst_idx_b = c->inst_idx_b;
-  a.proj_rec = c->proj_rec;
-  a.inst_rec = nullptr;
+  a.proj_rec = b.proj_rec;
+  a.inst_rec = b.inst_rec;
   return a;
 }
 
 template <int PASS>
-static void run_pass(gs_context *c, RadixArgs &a, uint64_t n_max) {
+static void run_pass(gs_context *c, RadixArgs &a, uint64_t n_max, cudaStream_t st) {
   const int grid = persistent_grid(c, n_max, kRadixTile, 8);
-  if (PASS != PASS_T1) k_radix_hist<PASS><<<grid, kRadixThreads, 0, c->stream>>>(a);
-  k_radix_scan<PASS><<<256, 256, 0, c->stream>>>(a);
-  k_radix_scatter<PASS><<<grid, kScatThreads, 0, c->stream>>>(a);
+  if (PASS != PASS_T1) k_radix_hist<PASS><<<grid, kRadixThreads, 0, st>>>(a);
+  k_radix_scan<PASS><<<256, 256, 0, st>>>(a);
+  k_radix_scatter<PASS><<<grid, kScatThreads, 0, st>>>(a);
 }
 
-// index.js:557-567 as two stable 8-bit passes -> c->order (6 launches)
-void launch_depth_radix(gs_context *c, FrameCounters *ctr) {
-  RadixArgs a = make_args(c, ctr);
+// index.js:557-567 as two stable 8-bit passes -> b.order (6 launches)
+void launch_depth_radix(gs_context *c, FrameCounters *ctr, const FrameBufs &b, cudaStream_t st) {
+  RadixArgs a = make_args(c, ctr, b);
   a.table = c->table_n;
   a.totals = c->totals;
   a.stride = c->table_n_stride;
-  run_pass<PASS_D1>(c, a, c->n);
-  run_pass<PASS_D2>(c, a, c->n);
+  run_pass<PASS_D1>(c, a, c->n, st);
+  run_pass<PASS_D2>(c, a, c->n, st);
 }
 
 // stable sort of the tile instances by tile id (5 launches: T1's histogram is produced by k_emit);
 // T2 writes the per-tile record lists
-void launch_tile_radix(gs_context *c, FrameCounters *ctr, float4 *inst_rec_out) {
-  RadixArgs a = make_args(c, ctr);
-  a.inst_rec = inst_rec_out;
+void launch_tile_radix(gs_context *c, FrameCounters *ctr, const FrameBufs &b, cudaStream_t st) {
+  RadixArgs a = make_args(c, ctr, b);
   a.table = c->table_d;
   a.totals = c->totals + 256;
   a.stride = c->table_d_stride;
-  run_pass<PASS_T1>(c, a, c->cap_inst);
-  run_pass<PASS_T2>(c, a, c->cap_inst);
+  run_pass<PASS_T1>(c, a, c->cap_inst, st);
+  run_pass<PASS_T2>(c, a, c->cap_inst, st);
 }
 
-void launch_tile_ranges(gs_context *c, FrameCounters *ctr, uint2 *tile_range_out) {
+void launch_tile_ranges(gs_context *c, FrameCounters *ctr, const FrameBufs &b, cudaStream_t st) {
   const int grid = persistent_grid(c, c->cap_inst, 256 * 8, 8);
-  k_tile_ranges<<<grid, 256, 0, c->stream>>>(c->inst_tile_f, ctr, tile_range_out);
+  k_tile_ranges<<<grid, 256, 0, st>>>(c->inst_tile_f, ctr, b.tile_range);
 }
 
 }  // namespace gs

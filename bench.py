@@ -11,7 +11,7 @@ N > 1: the same scene, the FRAME sharded by 16x16 screen tile over the ranks (ev
 splat table and the full draw order), one NCCL all-gather of finished RGBA8 tiles per frame -> strong scaling.
 
 `value` : frames/s with the scene resident in HBM and the frame left in HBM (device-timed: one CUDA-event pair around
-          the K steps on the library's stream, two frames in flight, L2 flushed between steps inside the region).
+          the K steps on the library's stream, three frames in flight, L2 flushed between steps inside the region).
 `e2e`   : frames/s through gs_render with HOST buffers: camera matrices in, RGBA8 frame out to pinned host memory,
           both copies inside the timed region.
 """
@@ -215,22 +215,22 @@ def run_ours(args):
     stream.synchronize()
 
     os.environ.setdefault("GS_BENCH", "1")
-    frames_dev = [frame_dev, torch.zeros_like(frame_dev)]
-    tiles_bufs = [tiles_dev, torch.zeros_like(tiles_dev)] if sharded else None
-    gath_bufs = [gathered, torch.zeros_like(gathered)] if sharded else None
+    frames_dev = [frame_dev, torch.zeros_like(frame_dev), torch.zeros_like(frame_dev)]
+    tiles_bufs = [tiles_dev, torch.zeros_like(tiles_dev), torch.zeros_like(tiles_dev)] if sharded else None
+    gath_bufs = [gathered, torch.zeros_like(gathered), torch.zeros_like(gathered)] if sharded else None
 
     def submit_device(i):
         """enqueue frame i on the library's stream (no host synchronisation); returns its ticket"""
         if not sharded:
-            return ctx.render_async(params, frames_dev[i & 1].data_ptr())
-        t = ctx.render_async(params, tiles_bufs[i & 1].data_ptr())
+            return ctx.render_async(params, frames_dev[i % 3].data_ptr())
+        t = ctx.render_async(params, tiles_bufs[i % 3].data_ptr())
         with torch.cuda.stream(stream):
-            dist.all_gather_into_tensor(gath_bufs[i & 1], tiles_bufs[i & 1])
-        ctx.assemble_tiles(gath_bufs[i & 1].data_ptr(), tiles_per_rank, world, w, h, gs.GS_FORMAT_RGBA8, frames_dev[i & 1].data_ptr())
+            dist.all_gather_into_tensor(gath_bufs[i % 3], tiles_bufs[i % 3])
+        ctx.assemble_tiles(gath_bufs[i % 3].data_ptr(), tiles_per_rank, world, w, h, gs.GS_FORMAT_RGBA8, frames_dev[i % 3].data_ptr())
         return t
 
     def run_pipeline(submit, steps, collect=None, per_step_events=True):
-        """K frames, at most two in flight.  Per-step CUDA-event pairs on the library's stream bracket each frame's
+        """K frames, at most three in flight.  Per-step CUDA-event pairs on the library's stream bracket each frame's
         device work (L2 flush outside the pair); a region pair brackets everything."""
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
         r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -244,13 +244,14 @@ def run_ours(args):
             tickets.append(submit(i))
             with torch.cuda.stream(stream):
                 b.record(stream)
-            if i >= 1:
-                st = ctx.wait(tickets[i - 1])
+            if i >= 2:  # three frames in flight: sort(i) | bin(i-1) | raster(i-2)
+                st = ctx.wait(tickets[i - 2])
                 if collect is not None:
                     collect.append(st.as_dict())
-        st = ctx.wait(tickets[-1])
-        if collect is not None:
-            collect.append(st.as_dict())
+        for t in tickets[max(0, len(tickets) - 2):]:
+            st = ctx.wait(t)
+            if collect is not None:
+                collect.append(st.as_dict())
         with torch.cuda.stream(stream):
             r1.record(stream)
         stream.synchronize()
@@ -268,7 +269,7 @@ def run_ours(args):
     # ---- value: device-resident frames ----
     stats = []
     barrier()
-    # whole-region time (one CUDA-event pair around all K steps, L2 flushes included): with two frames in flight the
+    # whole-region time (one CUDA-event pair around all K steps, L2 flushes included): with three frames in flight the
     # per-step pairs only see the raster stream and would hide the sort/bin work overlapped on the other stream
     _, total_ms = run_pipeline(submit_device, args.steps, stats)
     barrier()
@@ -280,7 +281,7 @@ def run_ours(args):
     ms_per_step = total_ms / args.steps
     fps = 1000.0 / ms_per_step
 
-    # ---- un-overlapped frames (one in flight) for the per-stage / roofline numbers: with two frames in flight the
+    # ---- un-overlapped frames (one in flight) for the per-stage / roofline numbers: with three frames in flight the
     #      stages of consecutive frames run concurrently and their individual durations stretch ----
     lat_stats = []
     for i in range(max(5, min(args.steps, 20))):
@@ -289,18 +290,18 @@ def run_ours(args):
         lat_stats.append(ctx.wait(submit_device(i)).as_dict())
 
     # ---- e2e: host buffers through the public C-ABI call, copies inside the timed region ----
-    host_frames = [ctx.pinned_array((h, w, 4), np.uint8), ctx.pinned_array((h, w, 4), np.uint8)]
+    host_frames = [ctx.pinned_array((h, w, 4), np.uint8) for _ in range(3)]
     if not sharded:
         p_host = ctx.make_params(fr, fmt=gs.GS_FORMAT_RGBA8, flags=0)
 
         def submit_host(i):
-            return ctx.render_async(p_host, host_frames[i & 1].ctypes.data)
+            return ctx.render_async(p_host, host_frames[i % 3].ctypes.data)
     else:
         def submit_host(i):
             t = submit_device(i)
             # frame back to pinned host memory, stream-ordered after the un-tiling
             with torch.cuda.stream(stream):
-                torch.from_numpy(host_frames[i & 1].reshape(-1)).copy_(frames_dev[i & 1], non_blocking=True)
+                torch.from_numpy(host_frames[i % 3].reshape(-1)).copy_(frames_dev[i % 3], non_blocking=True)
             return t
     run_pipeline(submit_host, 3)
     barrier()
@@ -313,7 +314,7 @@ def run_ours(args):
     e2e_ms = region_ms / args.steps
     e2e = {"value": 1000.0 / e2e_ms, "unit": "frames/s", "ms_per_step": e2e_ms,
            "h2d_bytes_per_step": C.sizeof(gs.GsRenderParams), "d2h_bytes_per_step": h * w * 4,
-           "note": "gs_render_async/gs_wait with host buffers, two frames in flight: the camera matrices go in as a "
+           "note": "gs_render_async/gs_wait with host buffers, three frames in flight: the camera matrices go in as a "
                    "400-byte H2D copy, the RGBA8 frame comes back to pinned host memory on a copy stream while the next "
                    "frame renders; the timed region (one CUDA-event pair around all K steps) includes every copy and the "
                    "L2 flushes between steps"}
@@ -366,8 +367,8 @@ def run_ours(args):
                          "algorithmic_bytes_per_launch": ab[dom], "ms_per_launch": stage_ms[dom],
                          "note": "k_raster is FP32-ALU bound (one exp + ~12 FMA per pixel-splat pair), reported against HBM as SURVEY.md 8d prescribes"},
             "stages": {k: roof(k) for k in stage_ms},
-            "pipeline": "two frames in flight: frame k is rasterised (low-priority stream) while frame k+1 is sorted and binned "
-                        "(high-priority stream); ms_per_step is the steady-state frame period, stages/roofline/frame are from "
+            "pipeline": "three frames in flight: frame k is rasterised (low-priority stream) while frame k+1 is binned and frame "
+                        "k+2 sorted/projected (high-priority streams); ms_per_step is the steady-state frame period, stages/roofline/frame are from "
                         "un-overlapped frames (one in flight) timed with the same CUDA events",
             "frame": {"bytes": ab["total"], "ms_device": st["ms_total"], "achieved_gbs": ab["total"] / (st["ms_total"] * 1e-3) / 1e9,
                       "frac": ab["total"] / (st["ms_total"] * 1e-3) / 1e9 / peak},

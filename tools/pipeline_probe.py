@@ -13,9 +13,9 @@ ctx.push_splats(rows)
 dev = torch.device("cuda", 0)
 stream = torch.cuda.ExternalStream(ctx._lib.gs_stream(ctx._h), device=dev)
 with torch.cuda.stream(stream):
-    fdev = [torch.zeros(h * w * 4, dtype=torch.uint8, device=dev) for _ in range(2)]
+    fdev = [torch.zeros(h * w * 4, dtype=torch.uint8, device=dev) for _ in range(3)]
     flush = torch.empty(160 << 20, dtype=torch.uint8, device=dev)
-host = [ctx.pinned_array((h, w, 4), np.uint8) for _ in range(2)]
+host = [ctx.pinned_array((h, w, 4), np.uint8) for _ in range(3)]
 pd = ctx.make_params(fr, flags=gs.GS_RENDER_OUT_DEVICE)
 ph = ctx.make_params(fr, flags=0)
 
@@ -30,14 +30,13 @@ def run(kind, steps=40, do_flush=False, depth=2):
             with torch.cuda.stream(stream):
                 flush.zero_()
         if kind == "dev":
-            tickets.append(ctx.render_async(pd, fdev[i & 1].data_ptr()))
+            tickets.append(ctx.render_async(pd, fdev[i % 3].data_ptr()))
         else:
-            tickets.append(ctx.render_async(ph, host[i & 1].ctypes.data))
-        if depth == 1:
-            ctx.wait(tickets[i])
-        elif i >= 1:
-            ctx.wait(tickets[i - 1])
-    ctx.wait(tickets[-1])
+            tickets.append(ctx.render_async(ph, host[i % 3].ctypes.data))
+        if i >= depth - 1:
+            ctx.wait(tickets[i - (depth - 1)])
+    for t in tickets[-(depth - 1):] if depth > 1 else []:
+        ctx.wait(t)
     with torch.cuda.stream(stream):
         r1.record(stream)
     stream.synchronize()
@@ -47,7 +46,7 @@ def run(kind, steps=40, do_flush=False, depth=2):
 for _ in range(2):
     for kind in ("dev", "host"):
         for fl in (False, True):
-            for depth in (1, 2):
+            for depth in (1, 2, 3):
                 ev, wall = run(kind, do_flush=fl, depth=depth)
                 print(f"{kind:5s} flush={fl!s:5s} depth={depth}: {ev:.4f} ms/frame (events)  {wall:.4f} ms/frame (wall)  dev ms_total={ctx.last_stats.ms_total:.4f}")
 # raw D2H bandwidth
