@@ -8,8 +8,8 @@ Only what the hot path needs lives here: `csrc/` (CUDA kernels + the C ABI), the
 host-side mirror of the reference's component interface, and the synthetic scene generator.
 """
 from . import _lib, build, dist, ply, scenes, three_math  # noqa: F401
-from ._lib import (GS_FORMAT_RGBA8, GS_FORMAT_RGBA32F, GS_RENDER_OUT_DEVICE, GS_RENDER_OUT_TILED,  # noqa: F401
-                   GS_RENDER_REUSE_SORT, GsRenderParams, GsStats)
+from ._lib import (GS_FORMAT_RGBA8, GS_FORMAT_RGBA32F, GS_RENDER_OUT_DEVICE, GS_RENDER_OUT_PEER,  # noqa: F401
+                   GS_RENDER_OUT_TILED, GS_RENDER_REUSE_SORT, GsRenderParams, GsStats)
 from .renderer import GsError, SplatContext  # noqa: F401
 from .scenes import FrameInputs, make_frame, synth_splats  # noqa: F401
 from .component import GaussianSplattingComponent, SortWorker  # noqa: F401

@@ -10,7 +10,7 @@ LIB_PATH = os.path.join(HERE, "libgsplat_b200.so")
 
 GS_OK, GS_ERR_INVALID, GS_ERR_CUDA, GS_ERR_OOM, GS_ERR_CAPACITY, GS_ERR_EMPTY = 0, -1, -2, -3, -4, -5
 GS_FORMAT_RGBA8, GS_FORMAT_RGBA32F = 0, 1
-GS_RENDER_OUT_DEVICE, GS_RENDER_REUSE_SORT, GS_RENDER_OUT_TILED = 1, 2, 4
+GS_RENDER_OUT_DEVICE, GS_RENDER_REUSE_SORT, GS_RENDER_OUT_TILED, GS_RENDER_OUT_PEER = 1, 2, 4, 8
 
 
 class GsStats(C.Structure):
@@ -56,6 +56,9 @@ SYMBOLS = {
     "gs_set_shard": (C.c_int, [_P, C.c_uint32, C.c_uint32]),
     "gs_owned_tiles": (C.c_uint32, [C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]),
     "gs_assemble_tiles": (C.c_int, [_P, _P, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int32, _P]),
+    "gs_peer_export": (C.c_int, [_P, C.c_size_t, _P]),
+    "gs_peer_import": (C.c_int, [_P, C.c_uint32, C.c_uint32, _P]),
+    "gs_peer_frame": (C.c_int, [_P, C.c_uint64, C.POINTER(_P)]),
     "gs_device_alloc": (C.c_int, [_P, C.c_size_t, C.POINTER(_P)]),
     "gs_device_free": (C.c_int, [_P, _P]),
     "gs_host_alloc": (C.c_int, [_P, C.c_size_t, C.POINTER(_P)]),

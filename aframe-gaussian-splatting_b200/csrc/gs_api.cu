@@ -79,7 +79,7 @@ static int ensure_table(gs_context *c, uint64_t need) {
 
 static int ensure_scratch(gs_context *c) {
   if (c->scratch_cap >= c->cap && c->depth) return GS_OK;
-  dev_free(c->depth); dev_free(c->idx_a); dev_free(c->dig_a); dev_free(c->table_n); dev_free(c->tile_total);
+  dev_free(c->depth); dev_free(c->idx_a); dev_free(c->dig_a); dev_free(c->table_n); dev_free(c->slice_total);
   for (int i = 0; i < 2; ++i) { dev_free(c->order[i]); dev_free(c->proj_rec[i]); dev_free(c->rect[i]); }
   dev_free(c->slice_prefix); dev_free(c->ent); dev_free(c->ent_off);
   const size_t n = c->cap;
@@ -93,7 +93,7 @@ static int ensure_scratch(gs_context *c) {
   }
   c->table_n_stride = (uint32_t)((n + kRadixTile - 1) / kRadixTile + 1);
   GS_CUDA(c, dev_alloc(&c->table_n, (size_t)256 * c->table_n_stride));
-  GS_CUDA(c, dev_alloc(&c->tile_total, (n + kEmitTile - 1) / kEmitTile + 1));
+  GS_CUDA(c, dev_alloc(&c->slice_total, (n + kEmitTile - 1) / kEmitTile + 1));
   GS_CUDA(c, dev_alloc(&c->slice_prefix, (n + kEmitTile - 1) / kEmitTile + 2));
   GS_CUDA(c, dev_alloc(&c->ent, n));
   GS_CUDA(c, dev_alloc(&c->ent_off, n));
@@ -143,7 +143,7 @@ static void drop_graphs(gs_context *c) {
   auto kill = [](cudaGraphExec_t &g) { if (g) { cudaGraphExecDestroy(g); g = nullptr; } };
   for (auto &sl : c->slot)
     for (int i = 0; i < 2; ++i) {
-      kill(sl.graph_a[i][0]); kill(sl.graph_a[i][1]); kill(sl.graph_b[i]); kill(sl.graph_r[i]);
+      kill(sl.graph_a[i][0]); kill(sl.graph_a[i][1]); kill(sl.graph_b[i]); kill(sl.graph_r[i]); kill(sl.graph_rp[i]);
     }
 }
 
@@ -250,7 +250,10 @@ extern "C" int gs_destroy(gs_context *c) {
   dev_free(c->tile_range[0]); dev_free(c->tile_range[1]); dev_free(c->quirk_table);
   if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
   drop_graphs(c);
-  dev_free(c->table_n); dev_free(c->table_d); dev_free(c->tile_total); dev_free(c->totals); dev_free(c->sort_hdr);
+  for (uint32_t r = 0; r < c->peer_world; ++r)
+    if (r != c->peer_rank && c->peer_base[r]) cudaIpcCloseMemHandle(c->peer_base[r]);
+  if (c->peer_local) cudaFree(c->peer_local);
+  dev_free(c->table_n); dev_free(c->table_d); dev_free(c->slice_total); dev_free(c->totals); dev_free(c->sort_hdr);
   dev_free(c->slice_prefix); dev_free(c->ent); dev_free(c->ent_off);
   for (auto &sl : c->slot) {
     dev_free(sl.ctr); dev_free(sl.fp);
@@ -497,9 +500,11 @@ static cudaError_t enqueue_raster_stage(gs_context *c, gs_context::Slot &sl, uin
     return external_events ? cudaEventRecordWithFlags(ev, st, cudaEventRecordExternal) : cudaEventRecord(ev, st);
   };
   cudaError_t e;
+  if (sl.peer) launch_peer_acquire(c, sl.fp, sl.ctr, c->rstream);
   if ((e = rec(sl.ev_r0, c->rstream))) return e;
   launch_raster(c, sl.fp, n_tiles, slot_bufs(c, sl), c->rstream);
   if ((e = rec(sl.ev[4], c->rstream))) return e;
+  if (sl.peer) launch_peer_signal_wait(c, sl.fp, sl.ctr, c->rstream);
   return cudaGetLastError();
 }
 
@@ -555,7 +560,8 @@ static int launch_frame(gs_context *c, gs_context::Slot &sl, bool reuse, uint32_
   c->sort_set_free[set] = sl.ev_binned;
   // C
   GS_CUDA(c, cudaStreamWaitEvent(c->rstream, sl.ev_binned, 0));
-  if ((rc = run_graph(c, sl.graph_r[set], c->rstream, [&](bool ext) { return enqueue_raster_stage(c, sl, n_tiles, ext); }))) return rc;
+  if ((rc = run_graph(c, sl.peer ? sl.graph_rp[set] : sl.graph_r[set], c->rstream,
+                      [&](bool ext) { return enqueue_raster_stage(c, sl, n_tiles, ext); }))) return rc;
   sl.launches = (reuse ? 0u : 7u) + 1u + 8u + 1u;
   return GS_OK;
 }
@@ -568,7 +574,7 @@ static int enqueue_readback(gs_context *c, gs_context::Slot &sl) {
   GS_CUDA(c, cudaStreamWaitEvent(c->copy_stream, sl.ev_done, 0));
   GS_CUDA(c, cudaMemcpyAsync(sl.ctr_host, sl.ctr, sizeof(FrameCounters), cudaMemcpyDeviceToHost, c->copy_stream));
   if (sl.host_out)
-    GS_CUDA(c, cudaMemcpyAsync(sl.out_user, sl.frame_dev, sl.out_bytes, cudaMemcpyDeviceToHost, c->copy_stream));
+    GS_CUDA(c, cudaMemcpyAsync(sl.out_user, sl.frame_src, sl.out_bytes, cudaMemcpyDeviceToHost, c->copy_stream));
   GS_CUDA(c, cudaEventRecord(sl.ev_copied, c->copy_stream));
   return GS_OK;
 }
@@ -603,11 +609,37 @@ static int submit(gs_context *c, gs_context::Slot &sl) {
   if (rc.out_tiled) out_pixels = (size_t)gs_owned_tiles(p->width, p->height, c->shard_rank, c->shard_world) * 256;
   sl.out_bytes = out_pixels * px_bytes;
   sl.host_out = !(p->flags & GS_RENDER_OUT_DEVICE);
-  if (sl.host_out) {
+  sl.peer = (p->flags & GS_RENDER_OUT_PEER) != 0;
+  if (sl.peer) {
+    if (!c->peer_world || c->peer_world != c->shard_world || c->peer_rank != c->shard_rank)
+      return fail(c, GS_ERR_INVALID, "GS_RENDER_OUT_PEER needs gs_peer_import with the rank/world of gs_set_shard");
+    if (rc.out_tiled) return fail(c, GS_ERR_INVALID, "GS_RENDER_OUT_PEER writes row-major frames: do not combine with GS_RENDER_OUT_TILED");
+    if (sl.out_bytes > c->peer_frame_bytes) return fail(c, GS_ERR_INVALID, "frame larger than the exported peer frame size");
+    // ring slot and sequence number come from the count of PEER frames, which every rank submits in the same order
+    // (tickets also count each rank's private frames, e.g. warm-up)
+    sl.ring = (int)(c->peer_count % 3);
+    sl.peer_seq = c->peer_count + 1;
+    fp.n_peer = c->peer_world;
+    fp.peer_rank = c->peer_rank;
+    for (uint32_t r = 0; r < c->peer_world; ++r) {
+      fp.peer_out[r] = peer_frame(c->peer_base[r], c->peer_frame_bytes, sl.ring);
+      fp.peer_done[r] = peer_done_row(c->peer_base[r], sl.ring);
+      fp.peer_released[r] = peer_released_row(c->peer_base[r], sl.ring);
+    }
+    fp.local_done = peer_done_row(c->peer_local, sl.ring);
+    fp.local_released = peer_released_row(c->peer_local, sl.ring);
+    fp.peer_seq = sl.peer_seq;
+    fp.peer_need = c->peer_count >= 3 ? c->peer_count - 2 : 0;  // sequence number of this ring slot's previous frame
+    fp.out = peer_frame(c->peer_local, c->peer_frame_bytes, sl.ring);
+    sl.frame_src = fp.out;
+    c->peer_count += 1;
+  } else if (sl.host_out) {
     if ((rcode = ensure_frame(c, sl, sl.out_bytes))) return rcode;
     fp.out = sl.frame_dev;
+    sl.frame_src = sl.frame_dev;
   } else {
     fp.out = sl.out_user;
+    sl.frame_src = nullptr;
   }
   const bool reuse = (p->flags & GS_RENDER_REUSE_SORT) && c->have_order;
   // a frame normally takes the buffer set the previous frame did not; a frame that reuses the last sort must read
@@ -626,6 +658,19 @@ static int wait_slot(gs_context *c, gs_context::Slot &sl, gs_stats *stats) {
   for (int attempt = 0;; ++attempt) {
     GS_CUDA(c, cudaEventSynchronize(sl.ev_copied));
     sl.pending = false;
+    if (sl.peer) {
+      // the frame has been published to (and consumed by) the other ranks: it cannot be silently re-run
+      const bool bad = sl.ctr_host->overflow || sl.ctr_host->peer_timeout;
+      PeerRows rows{};
+      for (uint32_t r = 0; r < c->peer_world; ++r) rows.p[r] = peer_released_row(c->peer_base[r], sl.ring);
+      launch_peer_release(c, rows, c->peer_world, c->peer_rank, sl.peer_seq, c->copy_stream);
+      GS_CUDA(c, cudaGetLastError());
+      if (sl.ctr_host->peer_timeout) return fail(c, GS_ERR_CUDA, "fused exchange: a peer did not signal in time");
+      if (sl.ctr_host->overflow)
+        return fail(c, GS_ERR_CAPACITY, "instance buffer overflow in a GS_RENDER_OUT_PEER frame: size the buffers with one plain frame first");
+      (void)bad;
+      break;
+    }
     if (!sl.ctr_host->overflow) break;
     if (attempt == 7) return fail(c, GS_ERR_CAPACITY, "instance buffer kept overflowing");
     // instance buffer too small: grow to the measured demand and run this frame again
@@ -680,6 +725,7 @@ extern "C" int gs_render_async(gs_context *c, const gs_render_params *p, void *o
   }
   sl.params = *p;
   sl.out_user = out_rgba;
+  sl.ticket = ticket;
   if ((rcode = submit(c, sl))) return rcode;
   c->next_ticket = ticket + 1;
   if (out_ticket) *out_ticket = ticket;
@@ -703,6 +749,47 @@ extern "C" int gs_render(gs_context *c, const gs_render_params *p, void *out_rgb
   int rc = gs_render_async(c, p, out_rgba, &t);
   if (rc) return rc;
   return gs_wait(c, t, stats);
+}
+
+extern "C" int gs_peer_export(gs_context *c, size_t frame_bytes, void *handle_out) {
+  if (!c || !handle_out || !frame_bytes) return GS_ERR_INVALID;
+  GS_CUDA(c, cudaSetDevice(c->device));
+  int rc = drain(c);
+  if (rc) return rc;
+  if (c->peer_local) return fail(c, GS_ERR_INVALID, "gs_peer_export: already exported");
+  frame_bytes = (frame_bytes + 4095) / 4096 * 4096;
+  const size_t total = kPeerFlagBytes + 3 * frame_bytes;
+  GS_CUDA(c, cudaMalloc(&c->peer_local, total));
+  GS_CUDA(c, cudaMemset(c->peer_local, 0, total));
+  c->peer_frame_bytes = frame_bytes;
+  cudaIpcMemHandle_t h;
+  GS_CUDA(c, cudaIpcGetMemHandle(&h, c->peer_local));
+  static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  memcpy(handle_out, &h, 64);
+  return GS_OK;
+}
+
+extern "C" int gs_peer_import(gs_context *c, uint32_t rank, uint32_t world, const void *handles) {
+  if (!c || !handles || world == 0 || world > (uint32_t)kMaxPeers || rank >= world) return GS_ERR_INVALID;
+  if (!c->peer_local) return fail(c, GS_ERR_INVALID, "gs_peer_import before gs_peer_export");
+  GS_CUDA(c, cudaSetDevice(c->device));
+  for (uint32_t r = 0; r < world; ++r) {
+    if (r == rank) { c->peer_base[r] = c->peer_local; continue; }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, (const char *)handles + 64 * (size_t)r, 64);
+    GS_CUDA(c, cudaIpcOpenMemHandle(&c->peer_base[r], h, cudaIpcMemLazyEnablePeerAccess));
+  }
+  c->peer_rank = rank;
+  c->peer_world = world;
+  return GS_OK;
+}
+
+extern "C" int gs_peer_frame(gs_context *c, uint64_t ticket, void **out) {
+  if (!c || !out || !c->peer_local || ticket >= c->next_ticket || ticket + 3 < c->next_ticket) return GS_ERR_INVALID;
+  const gs_context::Slot &sl = c->slot[ticket % 3];
+  if (!sl.peer || sl.ticket != ticket) return GS_ERR_INVALID;
+  *out = peer_frame(c->peer_local, c->peer_frame_bytes, sl.ring);
+  return GS_OK;
 }
 
 extern "C" int gs_get_stats(const gs_context *c, gs_stats *out) {

@@ -22,21 +22,12 @@ constexpr int kRadixItems = 16;
 constexpr int kRadixTile = kRadixThreads * kRadixItems;  // 4096 elements per look-back tile
 constexpr int kEmitThreads = 256;
 constexpr int kEmitItems = 1;
-constexpr int kEmitTile = kEmitThreads * kEmitItems;      // 256 sorted splats per emission slice (small: near splats own many more instances than far ones)
-constexpr uint32_t kInvalidDigit = 0xFFFFFFFFu;
+constexpr int kEmitTile = kEmitThreads * kEmitItems;      // 256 draw-order entries per slice of the instance-offset scan
+constexpr uint32_t kInvalidDigit = 0xFFFFFFFFu;  // element dropped by a radix pass
 constexpr uint32_t kNoRect = 0xFFFFFFFFu;
 constexpr uint16_t kNoTile = 0xFFFFu;
 // depth sentinel: a splat rejected by the worker filter (index.js:548 keeps only depth < 0)
 #define GS_DEPTH_REJECT 1.0f
-
-// look-back status word: 2 flag bits + 30 value bits
-constexpr uint32_t kFlagAgg = 1u << 30;
-constexpr uint32_t kFlagIncl = 2u << 30;
-constexpr uint32_t kFlagMask = 3u << 30;
-constexpr uint32_t kValMask = ~kFlagMask;
-constexpr unsigned long long kFlagAgg64 = 1ull << 62;
-constexpr unsigned long long kFlagIncl64 = 2ull << 62;
-constexpr unsigned long long kFlagMask64 = 3ull << 62;
 
 // Device-resident per-frame counters: zeroed by one memset at the start of every sort/render.
 struct FrameCounters {
@@ -49,6 +40,7 @@ struct FrameCounters {
   uint32_t n_visible;          // V2
   uint32_t n_inst_kept;        // instances surviving the exact footprint test and the tile-ownership filter
   uint32_t overflow;           // instance buffer too small: frame must be re-run
+  uint32_t peer_timeout;       // a peer flag was not seen in time (fused exchange)
   uint32_t count_done;         // k_count CTAs finished (the last one scans the slice totals)
 };
 
@@ -72,10 +64,22 @@ struct SortConsts {
 
 // Per-frame inputs, resident in device memory (one copy per pipeline slot) so that the whole frame is a static
 // CUDA graph: a 400-byte host->device copy of this struct is the only per-frame input traffic.
+constexpr int kMaxPeers = 16;
+
 struct FrameParams {
   SortConsts sc;
   RenderConsts rc;
   void *out;  // frame (or packed owned tiles) destination of the raster
+  // ---- fused raster + exchange over NVLink peer memory (GS_RENDER_OUT_PEER) ----
+  uint32_t n_peer;                       // 0: plain output; else every finished tile is stored into all ranks' frames
+  uint32_t peer_rank;
+  void *peer_out[kMaxPeers];             // this frame's slot in every rank's shared frame ring (own rank included)
+  unsigned long long *peer_done[kMaxPeers];      // rank r's done[slot][*] flag row (we write [.][peer_rank])
+  unsigned long long *peer_released[kMaxPeers];  // rank r's released[slot][*] flag row
+  unsigned long long *local_done;        // our done[slot][*]
+  unsigned long long *local_released;    // our released[slot][*]
+  unsigned long long peer_seq;           // ticket + 1 of this frame
+  unsigned long long peer_need;          // slot may be overwritten once every rank released seq >= peer_need
 };
 
 // preserved part of FrameCounters when a frame reuses the previous draw order
@@ -111,8 +115,8 @@ struct gs_context {
   uint32_t *table_n = nullptr;   // radix chunk histograms of the depth passes [256][table_n_stride]
   uint32_t table_n_stride = 0;
   uint32_t *totals = nullptr;    // [512]: digit totals of the depth / tile passes
-  uint32_t *tile_total = nullptr;    // instances per 256-entry slice of the draw order
-  uint32_t *slice_prefix = nullptr;  // exclusive scan of tile_total (+ total at the end)
+  uint32_t *slice_total = nullptr;   // instances per 256-entry slice of the draw order
+  uint32_t *slice_prefix = nullptr;  // exclusive scan of slice_total (+ total at the end)
   uint2 *ent = nullptr;              // per draw-order entry: {splat index, packed rect or kNoRect}
   uint32_t *ent_off = nullptr;       // per entry: exclusive instance offset inside its slice
 
@@ -150,6 +154,12 @@ struct gs_context {
     cudaGraphExec_t graph_a[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};  // sort + project, [set][reuse_sort]
     cudaGraphExec_t graph_b[2] = {nullptr, nullptr};                           // binning, [set]
     cudaGraphExec_t graph_r[2] = {nullptr, nullptr};                           // raster, [set]
+    cudaGraphExec_t graph_rp[2] = {nullptr, nullptr};                          // acquire + raster + signal/wait (fused exchange)
+    bool peer = false;
+    uint64_t ticket = 0;
+    int ring = 0;                            // slot of the shared frame ring (fused exchange)
+    unsigned long long peer_seq = 0;
+    void *frame_src = nullptr;               // device buffer the host copy reads
     cudaEvent_t ev_sorted = nullptr;                // sort/project stage of this slot's frame finished
     cudaEvent_t ev_binned = nullptr;                // binning stage finished
     cudaEvent_t ev_r0 = nullptr;                    // raster start (timing)
@@ -175,6 +185,13 @@ struct gs_context {
   // graph cache key: anything baked into the captured launches
   struct GraphKey { uint32_t n = 0, n_tiles = 0; uint64_t cap_inst = 0; const void *p0 = nullptr, *p1 = nullptr, *p2 = nullptr; } gkey;
 
+  // ---- fused exchange: one shared allocation per rank = flag rows + a ring of 3 frames, opened by every peer ----
+  void *peer_local = nullptr;            // our shared block
+  size_t peer_frame_bytes = 0;
+  void *peer_base[gs::kMaxPeers] = {};   // every rank's shared block as mapped here (own rank: peer_local)
+  uint32_t peer_world = 0, peer_rank = 0;
+  unsigned long long peer_count = 0;     // GS_RENDER_OUT_PEER frames submitted so far (identical on every rank)
+
   uint32_t shard_rank = 0, shard_world = 1;
   bool have_order = false;
   uint32_t order_count = 0;
@@ -183,6 +200,12 @@ struct gs_context {
 };
 
 namespace gs {
+
+// shared block layout: [done: 3 slots x kMaxPeers u64][released: 3 slots x kMaxPeers u64][pad to 4 KiB][frame 0][frame 1][frame 2]
+constexpr size_t kPeerFlagBytes = 4096;
+inline unsigned long long *peer_done_row(void *base, int slot) { return (unsigned long long *)base + (size_t)slot * kMaxPeers; }
+inline unsigned long long *peer_released_row(void *base, int slot) { return (unsigned long long *)base + (size_t)(3 + slot) * kMaxPeers; }
+inline void *peer_frame(void *base, size_t frame_bytes, int slot) { return (char *)base + kPeerFlagBytes + (size_t)slot * frame_bytes; }
 
 // buffers one frame's stages hand to each other (a pair of double-buffered sets)
 struct FrameBufs {
@@ -202,6 +225,11 @@ void launch_emit(gs_context *c, const FrameParams *fp, FrameCounters *ctr, const
 void launch_tile_radix(gs_context *c, FrameCounters *ctr, const FrameBufs &b, cudaStream_t st);  // 5 launches
 void launch_tile_ranges(gs_context *c, FrameCounters *ctr, const FrameBufs &b, cudaStream_t st);
 void launch_raster(gs_context *c, const FrameParams *fp, uint32_t n_tiles, const FrameBufs &b, cudaStream_t st);
+void launch_peer_acquire(gs_context *c, const FrameParams *fp, FrameCounters *ctr, cudaStream_t st);
+void launch_peer_signal_wait(gs_context *c, const FrameParams *fp, FrameCounters *ctr, cudaStream_t st);
+struct PeerRows { unsigned long long *p[kMaxPeers]; };
+void launch_peer_release(gs_context *c, const PeerRows &rows, uint32_t world, uint32_t rank, unsigned long long seq,
+                         cudaStream_t st);
 void launch_assemble(gs_context *c, const void *gathered, uint32_t tiles_per_rank, uint32_t world, uint32_t width,
                      uint32_t height, int32_t format, void *out_frame);
 
@@ -240,24 +268,6 @@ __host__ __device__ inline void owned_span(uint32_t tx0, uint32_t tx1, uint32_t 
                                            uint32_t &ncols) {
   first = tx0 + (rank + world - tx0 % world) % world;
   ncols = first <= tx1 ? (tx1 - first) / world + 1 : 0u;
-}
-
-__device__ __forceinline__ uint32_t ld_relaxed(const uint32_t *p) {
-  uint32_t v;
-  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_relaxed(uint32_t *p, uint32_t v) {
-  asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-
-__device__ __forceinline__ unsigned long long ld_relaxed64(const unsigned long long *p) {
-  unsigned long long v;
-  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_relaxed64(unsigned long long *p, unsigned long long v) {
-  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
 }  // namespace gs

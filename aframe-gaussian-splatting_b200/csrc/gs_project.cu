@@ -464,7 +464,7 @@ void launch_emit(gs_context *c, const FrameParams *fp, FrameCounters *ctr, const
   const uint64_t cap = (uint64_t)c->sm_count * 8;
   if (tiles > cap) tiles = cap;
   if (tiles < 1) tiles = 1;
-  k_count<<<(int)tiles, kEmitThreads, 0, st>>>(b.order, b.rect, c->ent, c->ent_off, c->tile_total,
+  k_count<<<(int)tiles, kEmitThreads, 0, st>>>(b.order, b.rect, c->ent, c->ent_off, c->slice_total,
                                                       c->slice_prefix, ctr, fp);
   uint64_t wins = (c->cap_inst + kEmitWindow - 1) / kEmitWindow;
   if (wins > (uint64_t)c->sm_count * 4) wins = (uint64_t)c->sm_count * 4;

@@ -161,13 +161,61 @@ __global__ void __launch_bounds__(256) k_raster(const float4 *__restrict__ inst_
     write = inside;
   }
   if (write) {
-    if (rc.out_format == GS_FORMAT_RGBA8) {
+    if (fp->n_peer) {
+      // fused exchange: the finished pixel goes straight into every rank's frame over NVLink peer stores, so the
+      // transfer overlaps the raster tile by tile and no collective / un-tiling pass follows
+      const uint32_t np = fp->n_peer;
+      if (rc.out_format == GS_FORMAT_RGBA8) {
+        const uint32_t v = to_u8(oR) | (to_u8(oG) << 8) | (to_u8(oB) << 16) | (to_u8(oA) << 24);
+        for (uint32_t r = 0; r < np; ++r) ((uint32_t *)fp->peer_out[r])[pix] = v;
+      } else {
+        const float4 v = make_float4(oR, oG, oB, oA);
+        for (uint32_t r = 0; r < np; ++r) ((float4 *)fp->peer_out[r])[pix] = v;
+      }
+    } else if (rc.out_format == GS_FORMAT_RGBA8) {
       const uint32_t v = inside ? (to_u8(oR) | (to_u8(oG) << 8) | (to_u8(oB) << 16) | (to_u8(oA) << 24)) : 0u;
       ((uint32_t *)out)[pix] = v;
     } else {
       ((float4 *)out)[pix] = inside ? make_float4(oR, oG, oB, oA) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
   }
+}
+
+// ---- fused-exchange flow control: two monotonic flag rows per frame slot, written over peer memory ----
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+// spin until *p >= need; gives up after ~2 s (a lost peer must not hang the GPU) and reports through ctr
+__device__ __forceinline__ void wait_flag(const unsigned long long *p, unsigned long long need, FrameCounters *ctr) {
+  const long long t0 = clock64();
+  while (ld_acquire_sys(p) < need) {
+    if (clock64() - t0 > 4000000000ll) { atomicExch(&ctr->peer_timeout, 1u); break; }
+    __nanosleep(200);
+  }
+}
+
+// before the raster may overwrite this slot of every rank's frame ring: all ranks have released its previous frame
+__global__ void k_peer_acquire(const FrameParams *__restrict__ fp, FrameCounters *ctr) {
+  if (threadIdx.x < fp->n_peer && fp->peer_need) wait_flag(fp->local_released + threadIdx.x, fp->peer_need, ctr);
+}
+
+// after the raster: tell every rank our tiles of this frame have landed, then wait for everybody else's
+__global__ void k_peer_signal_wait(const FrameParams *__restrict__ fp, FrameCounters *ctr) {
+  const uint32_t r = threadIdx.x;
+  if (r >= fp->n_peer) return;
+  __threadfence_system();
+  st_release_sys(fp->peer_done[r] + fp->peer_rank, fp->peer_seq);
+  wait_flag(fp->local_done + r, fp->peer_seq, ctr);
+}
+
+// when the host has consumed a frame (gs_wait): every rank may overwrite our copy of that slot
+__global__ void k_peer_release(PeerRows rows, uint32_t world, uint32_t rank, unsigned long long seq) {
+  if (threadIdx.x < world) st_release_sys(rows.p[threadIdx.x] + rank, seq);
 }
 
 // scatter `world` gathered tiled buffers back into a row-major frame (one thread per pixel)
@@ -190,6 +238,17 @@ __global__ void __launch_bounds__(256) k_assemble(const void *__restrict__ gathe
 
 void launch_raster(gs_context *c, const FrameParams *fp, uint32_t n_tiles, const FrameBufs &b, cudaStream_t st) {
   k_raster<<<n_tiles, 256, 0, st>>>(b.inst_rec, b.tile_range, fp);
+}
+
+void launch_peer_acquire(gs_context *c, const FrameParams *fp, FrameCounters *ctr, cudaStream_t st) {
+  k_peer_acquire<<<1, 32, 0, st>>>(fp, ctr);
+}
+void launch_peer_signal_wait(gs_context *c, const FrameParams *fp, FrameCounters *ctr, cudaStream_t st) {
+  k_peer_signal_wait<<<1, 32, 0, st>>>(fp, ctr);
+}
+void launch_peer_release(gs_context *c, const PeerRows &rows, uint32_t world, uint32_t rank, unsigned long long seq,
+                         cudaStream_t st) {
+  k_peer_release<<<1, 32, 0, st>>>(rows, world, rank, seq);
 }
 
 void launch_assemble(gs_context *c, const void *gathered, uint32_t tiles_per_rank, uint32_t world, uint32_t width,

@@ -2,9 +2,11 @@
 // and the stable LSD radix passes shared by the depth sort and the tile binning.
 //
 //   k_depth_cull  : index.js:517-555  depth (fp64, left to right), cutout box, filter, min/max
-//   k_key_hist    : index.js:557-563  16-bit key = ToInt32((f32 depth - min) * depthInv), digit histograms
-//   k_radix<D1/D2>: index.js:564-567  stable counting sort, as two 8-bit passes with decoupled look-back
-//   k_radix<T1/T2>: stable sort of tile instances by 16-bit tile id (T2 also gathers the 32 B records)
+//   k_radix_{hist,scan,scatter}<D1/D2>: index.js:557-567  16-bit key = ToInt32((f32 depth - min) * depthInv), stable
+//                   counting sort as two 8-bit passes
+//   k_radix_{scan,scatter}<T1>, k_radix_{hist,scan,scatter}<T2>: stable sort of tile instances by 16-bit tile id
+//                   (T1's histograms come from k_emit; T2 also gathers the 32 B records)
+//   k_tile_ranges : per-tile {start, end} in the final instance order
 //
 // Bit-exactness: JS evaluates in fp64 with IEEE rounding after every operation; the kernels use
 // __dmul_rn/__dadd_rn so nothing is contracted, and ToInt32 is restated exactly (js_to_int32).

@@ -170,6 +170,23 @@ class SplatContext:
         self._check(self._lib.gs_assemble_tiles(self._h, C.c_void_p(gathered_ptr), tiles_per_rank, world, width, height, fmt,
                                                 C.c_void_p(out_ptr)))
 
+    def peer_export(self, frame_bytes: int) -> bytes:
+        """gs_peer_export: allocate this rank's shared frame ring, return its 64-byte CUDA IPC handle."""
+        buf = C.create_string_buffer(64)
+        self._check(self._lib.gs_peer_export(self._h, frame_bytes, buf))
+        return buf.raw
+
+    def peer_import(self, rank: int, world: int, handles: list) -> None:
+        """gs_peer_import: map every rank's ring (handles in rank order, each 64 bytes)."""
+        blob = b"".join(handles)
+        assert len(blob) == 64 * world
+        self._check(self._lib.gs_peer_import(self._h, rank, world, C.c_char_p(blob)))
+
+    def peer_frame(self, ticket: int) -> int:
+        p = C.c_void_p()
+        self._check(self._lib.gs_peer_frame(self._h, ticket, C.byref(p)))
+        return p.value
+
     # -- memory helpers --
     def host_alloc(self, nbytes: int) -> int:
         p = C.c_void_p()

@@ -34,6 +34,12 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 METRIC = "frames/sec @1920x1080 (sort + splat raster, 1 M synthetic train-like splats)"
+METRICS = {
+    "train_1m_1080p": METRIC,
+    "bicycle_6m_1080p_orbit": "frames/sec @1920x1080 (sort + splat raster, 6 M synthetic splats, 360-degree orbit, re-sort per frame)",
+    "synth_20m_2160p_cutout": "frames/sec @3840x2160 (sort + splat raster, 20 M synthetic splats, cutout box)",
+    "synth_80m_1080p": "frames/sec @1920x1080 (sort + splat raster, 80 M synthetic splats)",
+}
 
 
 def load_peaks():
@@ -113,6 +119,8 @@ def build_scene(gs, args):
         n = args.splats
     rows = gs.synth_splats(n, seed)
     fr = sc.make_frame(sc.fixed_camera(w, h), sc.demo_object(), w, h, sc.demo_cutout() if cutout else None)
+    if "orbit" in args.workload:  # config 3: 120-step 360 degree yaw orbit, re-sorted every frame
+        build_scene.orbit = [sc.make_frame(sc.orbit_camera(w, h, i), sc.demo_object(), w, h) for i in range(120)]
     return rows, fr, n, w, h
 
 
@@ -188,8 +196,16 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # keep stdout to the one JSON line
-        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local))
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ.pop("NCCL_DEBUG")  # its banner goes to stdout; keep stdout to the one JSON line
+        # the all-gather of finished tiles is latency-critical and tiny: give NCCL's stream the same (highest) priority
+        # as the library's sort/bin streams, otherwise its kernels queue behind them on every rank and the ranks skew
+        opts = None
+        try:
+            opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
+        except Exception:
+            pass
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local), pg_options=opts)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU path")
     torch.cuda.set_device(local)
@@ -207,6 +223,9 @@ def run_ours(args):
 
     flags = gs.GS_RENDER_OUT_DEVICE | (gs.GS_RENDER_OUT_TILED if sharded else 0)
     params = ctx.make_params(fr, fmt=gs.GS_FORMAT_RGBA8, flags=flags)
+    orbit = getattr(build_scene, "orbit", None)
+    orbit_dev = [ctx.make_params(f, fmt=gs.GS_FORMAT_RGBA8, flags=flags) for f in orbit] if orbit else None
+    orbit_host = [ctx.make_params(f, fmt=gs.GS_FORMAT_RGBA8, flags=0) for f in orbit] if orbit else None
     with torch.cuda.stream(stream):
         frame_dev = torch.zeros(h * w * 4, dtype=torch.uint8, device=dev)
         tiles_dev = torch.zeros(tiles_per_rank * 1024, dtype=torch.uint8, device=dev) if sharded else None
@@ -219,11 +238,24 @@ def run_ours(args):
     tiles_bufs = [tiles_dev, torch.zeros_like(tiles_dev), torch.zeros_like(tiles_dev)] if sharded else None
     gath_bufs = [gathered, torch.zeros_like(gathered), torch.zeros_like(gathered)] if sharded else None
 
+    # ---- multi-GPU exchange: fused raster + peer stores over NVLink (default) or NCCL all-gather of tiles ----
+    use_peer = sharded and args.exchange == "p2p"
+    if use_peer:
+        handles = [None] * world
+        dist.all_gather_object(handles, ctx.peer_export(h * w * 4))
+        ctx.peer_import(rank, world, handles)
+        ctx.render_raw(ctx.make_params(fr, fmt=gs.GS_FORMAT_RGBA8, flags=gs.GS_RENDER_OUT_DEVICE), frames_dev[0].data_ptr())  # sizes the instance buffers
+        dist.barrier()
+        peer_dev = ctx.make_params(fr, fmt=gs.GS_FORMAT_RGBA8, flags=gs.GS_RENDER_OUT_DEVICE | gs.GS_RENDER_OUT_PEER)
+        peer_host = ctx.make_params(fr, fmt=gs.GS_FORMAT_RGBA8, flags=gs.GS_RENDER_OUT_PEER)
+
     def submit_device(i):
         """enqueue frame i on the library's stream (no host synchronisation); returns its ticket"""
+        if use_peer:
+            return ctx.render_async(peer_dev, 1)  # the assembled frame lands in every rank's shared ring
         if not sharded:
-            return ctx.render_async(params, frames_dev[i % 3].data_ptr())
-        t = ctx.render_async(params, tiles_bufs[i % 3].data_ptr())
+            return ctx.render_async(orbit_dev[i % 120] if orbit_dev else params, frames_dev[i % 3].data_ptr())
+        t = ctx.render_async(orbit_dev[i % 120] if orbit_dev else params, tiles_bufs[i % 3].data_ptr())
         with torch.cuda.stream(stream):
             dist.all_gather_into_tensor(gath_bufs[i % 3], tiles_bufs[i % 3])
         ctx.assemble_tiles(gath_bufs[i % 3].data_ptr(), tiles_per_rank, world, w, h, gs.GS_FORMAT_RGBA8, frames_dev[i % 3].data_ptr())
@@ -295,7 +327,10 @@ def run_ours(args):
         p_host = ctx.make_params(fr, fmt=gs.GS_FORMAT_RGBA8, flags=0)
 
         def submit_host(i):
-            return ctx.render_async(p_host, host_frames[i % 3].ctypes.data)
+            return ctx.render_async(orbit_host[i % 120] if orbit_host else p_host, host_frames[i % 3].ctypes.data)
+    elif use_peer:
+        def submit_host(i):
+            return ctx.render_async(peer_host, host_frames[i % 3].ctypes.data)
     else:
         def submit_host(i):
             t = submit_device(i)
@@ -349,16 +384,16 @@ def run_ours(args):
                 traffic = None
         r = roof(dom)
         line = {
-            "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "metric": METRICS.get(args.workload, METRIC), "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64 sort keys + f32 shading", "data": "synthetic",
-            "config": {"workload": args.workload, "n_splats": n, "width": w, "height": h, "camera": "fixed",
-                       "parallelism": "1 GPU" if world == 1 else f"screen-tile sharding x{world} + NCCL all-gather of RGBA8 tiles",
+            "config": {"workload": args.workload, "n_splats": n, "width": w, "height": h, "camera": "orbit-120" if orbit else "fixed",
+                       "parallelism": "1 GPU" if world == 1 else (f"screen-tile-column sharding x{world}, raster fused with the exchange: finished tiles stored into every rank's frame over NVLink peer memory" if use_peer else f"screen-tile-column sharding x{world} + NCCL all-gather of RGBA8 tiles"),
                        "l2": "flushed between timed steps (160 MiB memset on the raster stream, INSIDE the timed region)",
                        "counters": {k: st[k] for k in ("n_splats", "n_sorted", "n_visible", "n_instances", "n_instances_kept", "n_tiles")}},
             "msplats_per_s": n * fps / 1e6,
             "e2e": e2e,
-            "gpu_launches": int(st["kernel_launches"]) * args.steps + (args.steps if sharded else 0),
+            "gpu_launches": (int(st["kernel_launches"]) + (2 if use_peer else (1 if sharded else 0))) * args.steps,
             "clocks": clocks,
             "roofline": {"kernel": {"sort": "k_depth_cull+k_radix_{hist,scan,scatter}<D1,D2>", "project": "k_project", "bin": "k_count+k_emit+k_radix_{hist,scan,scatter}<T1,T2>+k_tile_scan",
                                     "raster": "k_raster"}[dom],
@@ -405,6 +440,8 @@ def main():
     ap.add_argument("--workload", default="train_1m_1080p")
     ap.add_argument("--splats", type=int, default=0, help="override the workload's splat count (debug)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
+                    help="multi-GPU frame exchange: fused raster + NVLink peer stores (default) or NCCL all-gather of tiles")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

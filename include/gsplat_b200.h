@@ -56,8 +56,11 @@ enum {
   GS_RENDER_REUSE_SORT = 1u << 1, /* reuse the draw order of the previous gs_sort/gs_render
                                      (reference behaviour when sortReady is false,
                                      index.js:206,439-440: the draw uses a stale order)       */
-  GS_RENDER_OUT_TILED = 1u << 2   /* multi-GPU: write only the tiles this rank owns, packed as
+  GS_RENDER_OUT_TILED = 1u << 2,  /* multi-GPU: write only the tiles this rank owns, packed as
                                      16x16 RGBA blocks in owned-tile order (see gs_set_shard) */
+  GS_RENDER_OUT_PEER = 1u << 3    /* multi-GPU, fused raster + exchange: every finished tile is stored
+                                     straight into ALL ranks' frames over NVLink peer memory (see
+                                     gs_peer_export / gs_peer_import); no collective, no un-tiling */
 };
 
 /* Per-frame counters (SURVEY.md 8d symbols) and device timings of the last gs_sort/gs_render */
@@ -182,6 +185,19 @@ GS_API uint32_t gs_owned_tiles(uint32_t width, uint32_t height, uint32_t rank, u
  * gathered / out_frame are device pointers.  Stream-ordered on gs_stream(ctx); call gs_synchronize to wait. */
 GS_API int gs_assemble_tiles(gs_context *ctx, const void *gathered, uint32_t tiles_per_rank, uint32_t world,
                              uint32_t width, uint32_t height, int32_t format, void *out_frame);
+
+/*
+ * Fused raster + exchange (one process per GPU, same node).  Each rank calls gs_peer_export, the 64-byte handles
+ * are exchanged by the host program (any transport; bench.py uses torch.distributed), then every rank calls
+ * gs_peer_import with all `world` handles in rank order.  A gs_render_async with GS_RENDER_OUT_PEER then leaves the
+ * complete frame in this rank's shared ring (gs_peer_frame), and also copies it to out_rgba when that is host
+ * memory.  Flow control: a frame slot is rewritten only after every rank's gs_wait released its previous frame.
+ */
+GS_API int gs_peer_export(gs_context *ctx, size_t frame_bytes, void *ipc_handle_out64);
+GS_API int gs_peer_import(gs_context *ctx, uint32_t rank, uint32_t world, const void *ipc_handles_world_x64);
+/* device pointer of the assembled frame of `ticket` inside this rank's shared ring (valid until the third
+ * following gs_render_async) */
+GS_API int gs_peer_frame(gs_context *ctx, uint64_t ticket, void **out_dev_ptr);
 
 /* Device-memory helpers so a host language without a CUDA binding can keep frames on the GPU. */
 GS_API int gs_device_alloc(gs_context *ctx, size_t bytes, void **out_dev_ptr);
