@@ -290,6 +290,7 @@ __global__ void __launch_bounds__(kEmitThreads, 4) k_emit(const uint2 *__restric
   __shared__ float4 s_g0[kEmitEnt];         // cx, cy, a1x, a1y
   __shared__ float2 s_g1[kEmitEnt];         // a2x, a2y
   __shared__ uint32_t s_jfl[2];
+  __shared__ uint32_t s_cnt[kEmitThreads / 32];
   __shared__ uint32_t s_hist[256];  // low tile-id byte of the kept instances of this window: pass T1's histogram column
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   s_hist[tid] = 0;
@@ -323,24 +324,40 @@ __global__ void __launch_bounds__(kEmitThreads, 4) k_emit(const uint2 *__restric
     const uint32_t j_last = s_jfl[1];
     uint32_t j0 = s_jfl[0], pos = wb;
     while (pos < we) {
-      // ---- 2. stage entries [j0, jE) ----
-      const uint32_t jE = min(j0 + (uint32_t)kEmitEnt, j_last + 1);
-      const uint32_t nE = jE - j0;
-      for (uint32_t i = tid; i <= nE; i += kEmitThreads) {
-        s_goff[i] = goff(j0 + i);
-        if (i < nE) {
-          const uint2 en = __ldg(ent + j0 + i);
-          s_ent[i] = en;
+      // ---- 2. stage the entries that own tiles, compacted in order, from source entries [j0, ...) ----
+      // (with the frame sharded over GPUs most entries own no tile of this rank: skipping them here keeps the
+      //  staged window dense); batches of 256 source entries until the staging arrays are full
+      uint32_t nE = 0, jn = j0;
+      while (jn <= j_last && nE + kEmitThreads <= (uint32_t)kEmitEnt) {
+        const uint32_t j = jn + tid;
+        uint2 en = make_uint2(0u, kNoRect);
+        if (j <= j_last) en = __ldg(ent + j);
+        const bool nz = en.y != kNoRect;
+        const uint32_t bal = __ballot_sync(0xffffffffu, nz);
+        if (lane == 0) s_cnt[warp] = __popc(bal);
+        __syncthreads();
+        uint32_t base_w = nE, tot = 0;
+        for (uint32_t k2 = 0; k2 < kEmitThreads / 32; ++k2) {
+          if (k2 < warp) base_w += s_cnt[k2];
+          tot += s_cnt[k2];
+        }
+        if (nz) {
+          const uint32_t q = base_w + __popc(bal & ((1u << lane) - 1u));
+          s_ent[q] = en;
+          s_goff[q] = goff(j);
           const uint32_t r = en.y;
-          if (r != kNoRect) {
-            const uint32_t wfull = ((r >> 8) & 255u) - (r & 255u) + 1u, hfull = (r >> 24) - ((r >> 16) & 255u) + 1u;
-            if (wfull * hfull > 1u) {  // footprint geometry for the exact tile test
-              s_g0[i] = __ldg(proj_rec + 2 * (size_t)en.x);
-              s_g1[i] = __ldg((const float2 *)(proj_rec + 2 * (size_t)en.x + 1));
-            }
+          const uint32_t wfull = ((r >> 8) & 255u) - (r & 255u) + 1u, hfull = (r >> 24) - ((r >> 16) & 255u) + 1u;
+          if (wfull * hfull > 1u) {  // footprint geometry for the exact tile test
+            s_g0[q] = __ldg(proj_rec + 2 * (size_t)en.x);
+            s_g1[q] = __ldg((const float2 *)(proj_rec + 2 * (size_t)en.x + 1));
           }
         }
+        nE += tot;
+        jn += kEmitThreads;
+        __syncthreads();
       }
+      const uint32_t jE = min(jn, j_last + 1);
+      if (tid == 0) s_goff[nE] = goff(jE);  // first position NOT covered by the staged entries
       __syncthreads();
       const uint32_t pe = min(we, s_goff[nE]);  // positions [pos, pe) belong to the staged entries
       // ---- 3. generate ----
@@ -391,7 +408,7 @@ __global__ void __launch_bounds__(kEmitThreads, 4) k_emit(const uint2 *__restric
         load_entry(e, k);
 #pragma unroll 1
         for (uint32_t p = t0; p < t1; ++p) {
-          while (k >= n_own) {  // next staged entry that owns tiles
+          if (k >= n_own) {  // next staged entry (every staged entry owns tiles)
             ++e;
             load_entry(e, 0u);
             k = 0;
