@@ -90,3 +90,13 @@ def test_component_schema_matches_reference(gs):
     assert set(s) == {"src", "cutoutEntity", "pixelRatio", "xrPixelRatio"}
     for name in ("init", "initGL", "loadData", "pushDataBuffer", "tick", "getProjectionMatrix", "getModelViewMatrix", "processPlyBuffer"):
         assert callable(getattr(gs.GaussianSplattingComponent, name))
+
+
+def test_header_is_plain_c_and_example_compiles():
+    """include/gsplat_b200.h must be consumable from C99 (the FFI boundary), and the C example must compile
+    against it (syntax + types only: no CUDA needed)."""
+    import subprocess
+    ex = os.path.join(ROOT, "examples", "render_frame.c")
+    res = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-fsyntax-only", "-I", os.path.join(ROOT, "include"), ex],
+                         capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
