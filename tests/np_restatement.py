@@ -31,7 +31,11 @@ def np_sort(matrices, view, cutout=None):
         inv = 65535.0 / (mx - mn)
         val = (d32 - mn) * inv
     val = np.where(np.isfinite(val), val, 0.0)
-    key = np.trunc(val).astype(np.int64)  # ToInt32 (no wrap needed in the tested ranges)
+    # ToInt32: truncate, wrap modulo 2^32, reinterpret as signed (fmod of doubles is exact)
+    w = np.fmod(np.trunc(val), 4294967296.0)
+    w = np.where(w < 0, w + 4294967296.0, w)
+    key = w.astype(np.int64)
+    key = np.where(key >= 2147483648, key - 4294967296, key)
     ok = (key >= 0) & (key <= 65535)
     order = np.argsort(key[ok], kind="stable")
     out = np.zeros(len(idx), np.uint32)
