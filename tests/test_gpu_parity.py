@@ -318,3 +318,36 @@ def test_full_size_properties(gs, ctx):
     assert np.allclose(fb[..., 0], f32[..., 0] + T, atol=2e-6) and np.allclose(fb[..., 3], 1.0, atol=2e-6)
     st = ctx.stats()
     assert st["n_splats"] == n and st["n_instances"] > st["n_visible"] > 0
+
+
+def test_sort_exact_random_regimes(orc, ctx):
+    """Bit-exact sort over the regimes that stress the fp64 / ToInt32 restatement: heavy ties, depth ranges below f32
+    resolution (keys wrap or leave [0, 65535], quirk Q5), 40 decades of magnitudes, tricky view vectors, cutouts."""
+    tricky = [0.0, -0.0, 1e-30, -1e-30, 1e-45, 1.0, -1.0, 3.4e38, -3.4e38, 1e-6, 65535.0, 0.5]
+    for seed in range(24):
+        rng = np.random.default_rng(1000 + seed)
+        n = int(rng.integers(1, 30000))
+        mode = ["random", "ties", "narrow", "wide"][seed % 4]
+        m = np.zeros((n, 16), np.float32)
+        if mode == "random":
+            m[:, 12:15] = rng.normal(0, 5, (n, 3))
+        elif mode == "ties":
+            m[:, 12:15] = rng.integers(-2, 3, (n, 3))
+        elif mode == "narrow":
+            m[:, 12:15] = 1000.0 + rng.normal(0, 1e-5, (n, 3))
+        else:
+            m[:, 12:15] = rng.normal(0, 1, (n, 3)) * 10.0 ** rng.integers(-20, 20, (n, 1))
+        m[:, 15] = np.abs(rng.normal(0, 1, n)) * rng.integers(0, 2, n)
+        view = rng.normal(0, 1, 4).astype(np.float32)
+        if seed % 3 == 0:
+            view[rng.integers(0, 4)] = tricky[seed % len(tricky)]
+        cut = None
+        if seed % 2:
+            c = np.eye(4, dtype=np.float32)
+            c[:3, :3] *= rng.uniform(0.05, 2.0, 3).astype(np.float32)
+            c[3, :3] = rng.normal(0, 1, 3)
+            cut = c.reshape(16)
+        cs = np.zeros((n, 4), np.float32); cs[:, :3] = m[:, 12:15]
+        ctx.clear(); ctx.push_packed(cs, np.zeros((n, 4), np.uint32), m[:, 15])
+        got, exp = ctx.sort(view, cut), orc.sort(m, view, cut)
+        assert np.array_equal(got, exp), (seed, mode, n, len(got), len(exp))
