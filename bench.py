@@ -395,7 +395,7 @@ def run_ours(args):
             "e2e": e2e,
             "gpu_launches": (int(st["kernel_launches"]) + (2 if use_peer else (1 if sharded else 0))) * args.steps,
             "clocks": clocks,
-            "roofline": {"kernel": {"sort": "k_depth_cull+k_radix_{hist,scan,scatter}<D1,D2>", "project": "k_project", "bin": "k_count+k_emit+k_radix_{hist,scan,scatter}<T1,T2>+k_tile_scan",
+            "roofline": {"kernel": {"sort": "k_depth_cull+k_radix_{hist,scan,scatter}<D1,D2>", "project": "k_project", "bin": "k_count+k_emit+k_radix_{scan,scatter}<T1>+k_radix_{hist,scan,scatter}<T2>+k_tile_ranges",
                                     "raster": "k_raster"}[dom],
                          "bound": "hbm", "achieved": r["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": r["frac"],
                          "traffic": traffic, "peak_source": peak_src,
