@@ -438,8 +438,6 @@ extern "C" uint32_t gs_owned_tiles(uint32_t width, uint32_t height, uint32_t ran
   return owned_tiles_host(width, height, rank, world);
 }
 
-// Everything one frame does on the main stream; all per-frame inputs come from sl.fp (device memory), so the same
-// sequence can be captured once into a CUDA graph and replayed.
 static FrameBufs slot_bufs(gs_context *c, const gs_context::Slot &sl) {
   return FrameBufs{c->order[sl.set], c->proj_rec[sl.set], c->rect[sl.set], c->inst_rec[sl.set], c->tile_range[sl.set]};
 }

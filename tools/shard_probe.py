@@ -1,5 +1,6 @@
+"""GPU probe: per-stage device times of rank 0 of a 1/2/8-way tile-column sharding, emulated on one GPU."""
 import importlib, os, sys, numpy as np
-sys.path.insert(0, "/root/repo")
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 gs = importlib.import_module("aframe-gaussian-splatting_b200")
 sc = gs.scenes
 n, w, h, seed, _ = sc.CONFIGS["train_1m_1080p"]
