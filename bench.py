@@ -241,9 +241,19 @@ def run_ours(args):
     # ---- multi-GPU exchange: fused raster + peer stores over NVLink (default) or NCCL all-gather of tiles ----
     use_peer = sharded and args.exchange == "p2p"
     if use_peer:
-        handles = [None] * world
-        dist.all_gather_object(handles, ctx.peer_export(h * w * 4))
-        ctx.peer_import(rank, world, handles)
+        # every rank must take the same path: agree on whether the peer mapping worked everywhere, else use NCCL
+        ok = 1
+        try:
+            handles = [None] * world
+            dist.all_gather_object(handles, ctx.peer_export(h * w * 4))
+            ctx.peer_import(rank, world, handles)
+        except Exception as e:  # no peer access / IPC on this box
+            sys.stderr.write(f"[rank {rank}] fused exchange unavailable ({e}); falling back to the NCCL all-gather\n")
+            ok = 0
+        flag = torch.tensor([ok], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        use_peer = bool(flag.item())
+    if use_peer:
         ctx.render_raw(ctx.make_params(fr, fmt=gs.GS_FORMAT_RGBA8, flags=gs.GS_RENDER_OUT_DEVICE), frames_dev[0].data_ptr())  # sizes the instance buffers
         dist.barrier()
         peer_dev = ctx.make_params(fr, fmt=gs.GS_FORMAT_RGBA8, flags=gs.GS_RENDER_OUT_DEVICE | gs.GS_RENDER_OUT_PEER)
