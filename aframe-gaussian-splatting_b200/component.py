@@ -13,6 +13,7 @@ What disappears on the GPU: the worker's `sortedIndexes` never leave the device 
 """
 from __future__ import annotations
 
+import math
 import os
 from typing import Callable, Optional
 
@@ -164,7 +165,9 @@ class GaussianSplattingComponent:
     def frame_inputs(self, width: int, height: int, camera=None) -> FrameInputs:
         proj = self.getProjectionMatrix(camera)
         mv = self.getModelViewMatrix(camera)
-        w, h = int(round(width * self.pixelRatio)), int(round(height * self.pixelRatio))
+        # renderer.setPixelRatio: three.js floors the drawing-buffer size and the current viewport
+        # (Math.floor(width * pixelRatio), viewport.multiplyScalar(pixelRatio).floor())
+        w, h = int(math.floor(width * self.pixelRatio)), int(math.floor(height * self.pixelRatio))
         cut = None
         if self.cutout is not None:
             cut = np.asarray(world_to_cutout(self.cutout, self.object).elements, dtype=np.float32)

@@ -374,13 +374,13 @@ static int drain(gs_context *c) {
 static void stats_from_counters(gs_context *c, const FrameCounters &h) {
   gs_stats &s = c->stats;
   s.n_splats = c->n;
-  s.n_sorted = h.n_valid;
-  s.n_dropped = h.n_dropped;
+  s.n_sorted = h.sort.n_valid;
+  s.n_dropped = h.sort.n_dropped;
   s.n_visible = h.n_visible;
   s.n_instances = h.n_inst;
   s.n_instances_kept = h.n_inst_kept;
-  s.min_depth = h.n_valid ? dec_f64(~h.min_enc) : INFINITY;
-  s.max_depth = h.n_valid ? dec_f64(h.max_enc) : -INFINITY;
+  s.min_depth = h.sort.n_valid ? dec_f64(~h.sort.min_enc) : INFINITY;
+  s.max_depth = h.sort.n_valid ? dec_f64(h.sort.max_enc) : -INFINITY;
 }
 
 extern "C" int gs_sort(gs_context *c, const float view[4], const float *cutout16_or_null, uint32_t *out_idx,
@@ -416,7 +416,7 @@ extern "C" int gs_sort(gs_context *c, const float view[4], const float *cutout16
   c->stats.ms_sort = ms;
   c->stats.ms_total = ms;
   c->have_order = true;
-  c->order_count = sl.ctr_host->n_valid;
+  c->order_count = sl.ctr_host->sort.n_valid;
   if (out_count) *out_count = c->order_count;
   if (out_idx && c->order_count)
     GS_CUDA(c, cudaMemcpy(out_idx, c->order[c->last_set], sizeof(uint32_t) * (size_t)c->order_count, cudaMemcpyDeviceToHost));
@@ -671,13 +671,28 @@ static int wait_slot(gs_context *c, gs_context::Slot &sl, gs_stats *stats) {
     }
     if (!sl.ctr_host->overflow) break;
     if (attempt == 7) return fail(c, GS_ERR_CAPACITY, "instance buffer kept overflowing");
-    // instance buffer too small: grow to the measured demand and run this frame again
-    const uint64_t need = std::max<uint64_t>(sl.ctr_host->n_inst + sl.ctr_host->n_inst / 8, c->cap_inst * 2);
+    // Instance buffer too small.  Frames submitted BEFORE this one that are still pending saw the same small
+    // buffer: finish (and, if needed, re-run) them first so frames are always re-run in submission order and
+    // last_set / have_order end up describing the most recently submitted frame.
+    for (;;) {
+      gs_context::Slot *older = nullptr;
+      for (auto &o : c->slot)
+        if (&o != &sl && o.pending && o.ticket < sl.ticket && (!older || o.ticket < older->ticket)) older = &o;
+      if (!older) break;
+      int rc_old = wait_slot(c, *older, nullptr);
+      if (rc_old) return rc_old;
+    }
     GS_CUDA(c, cudaStreamSynchronize(c->stream));  // the other slots' frames may still be using the buffers
     GS_CUDA(c, cudaStreamSynchronize(c->bstream));
     GS_CUDA(c, cudaStreamSynchronize(c->rstream));
-    int rcode = ensure_instances(c, need);
-    if (rcode) return rcode;
+    // grow once to the measured demand (+12.5 %); a frame whose overflow flag is stale (an earlier frame's regrow
+    // already made room) is simply run again
+    if (sl.ctr_host->n_inst > c->cap_inst) {
+      const uint64_t need = std::max<uint64_t>(sl.ctr_host->n_inst + sl.ctr_host->n_inst / 8, c->cap_inst + c->cap_inst / 2);
+      int rcode = ensure_instances(c, need);
+      if (rcode) return rcode;
+    }
+    int rcode;
     if ((rcode = submit(c, sl))) return rcode;
   }
   memset(&c->stats, 0, sizeof(c->stats));
@@ -691,7 +706,7 @@ static int wait_slot(gs_context *c, gs_context::Slot &sl, gs_stats *stats) {
   cudaEventElapsedTime(&c->stats.ms_bin, sl.ev[2], sl.ev[3]);  // on the bin stream
   cudaEventElapsedTime(&c->stats.ms_raster, sl.ev_r0, sl.ev[4]);
   cudaEventElapsedTime(&c->stats.ms_total, sl.ev[0], sl.ev[4]);
-  c->order_count = sl.ctr_host->n_valid;
+  c->order_count = sl.ctr_host->sort.n_valid;
   if (stats) *stats = c->stats;
   return GS_OK;
 }

@@ -8,6 +8,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stddef.h>
 #include <string.h>
 
 #include <string>
@@ -29,20 +30,29 @@ constexpr uint16_t kNoTile = 0xFFFFu;
 // depth sentinel: a splat rejected by the worker filter (index.js:548 keeps only depth < 0)
 #define GS_DEPTH_REJECT 1.0f
 
-// Device-resident per-frame counters: zeroed by one memset at the start of every sort/render.
-struct FrameCounters {
+// preserved part of FrameCounters when a frame reuses the previous draw order (GS_RENDER_REUSE_SORT): the sort's own
+// results.  FrameCounters starts with exactly this header, so a sizeof(SortHeader) device copy saves / restores it.
+struct SortHeader {
   unsigned long long min_enc;  // bit-inverted order-preserving encoding of the fp64 min depth (atomicMax)
   unsigned long long max_enc;  // order-preserving encoding of the fp64 max depth (atomicMax)
-  unsigned long long n_inst;   // D: emitted tile instances (bounding-rectangle candidates)
   uint32_t n_valid;            // V: splats passing the worker filter
   uint32_t n_inrange;          // V - dropped: entries with a key in [0,65535]
   uint32_t n_dropped;          // quirk Q5
+  uint32_t pad;
+};
+
+// Device-resident per-frame counters: zeroed by one memset at the start of every sort/render.
+struct FrameCounters {
+  SortHeader sort;             // min_enc, max_enc, n_valid, n_inrange, n_dropped
+  unsigned long long n_inst;   // D: emitted tile instances (bounding-rectangle candidates)
   uint32_t n_visible;          // V2
   uint32_t n_inst_kept;        // instances surviving the exact footprint test and the tile-ownership filter
   uint32_t overflow;           // instance buffer too small: frame must be re-run
   uint32_t peer_timeout;       // a peer flag was not seen in time (fused exchange)
   uint32_t count_done;         // k_count CTAs finished (the last one scans the slice totals)
+  uint32_t pad;
 };
+static_assert(offsetof(FrameCounters, sort) == 0 && sizeof(SortHeader) == 32, "SortHeader is the prefix of FrameCounters");
 
 struct RenderConsts {
   float proj[16];
@@ -82,11 +92,6 @@ struct FrameParams {
   unsigned long long peer_need;          // slot may be overwritten once every rank released seq >= peer_need
 };
 
-// preserved part of FrameCounters when a frame reuses the previous draw order
-struct SortHeader {
-  unsigned long long min_enc, max_enc;
-  uint32_t n_valid, n_inrange, n_dropped, pad;
-};
 
 }  // namespace gs
 

@@ -173,7 +173,7 @@ __global__ void __launch_bounds__(kEmitThreads) k_count(const uint32_t *__restri
   __shared__ uint32_t s_warp[kEmitThreads / 32], s_vis[kEmitThreads / 32];
   __shared__ uint32_t s_last;
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const uint32_t nv = ctr->n_valid;
+  const uint32_t nv = ctr->sort.n_valid;
   const uint32_t num_slices = (nv + kEmitTile - 1) / kEmitTile;
   for (uint32_t sl = blockIdx.x; sl < num_slices; sl += gridDim.x) {
     const uint32_t j = sl * kEmitTile + tid;
@@ -294,7 +294,7 @@ __global__ void __launch_bounds__(kEmitThreads, 4) k_emit(const uint2 *__restric
   __shared__ uint32_t s_hist[256];  // low tile-id byte of the kept instances of this window: pass T1's histogram column
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   s_hist[tid] = 0;
-  const uint32_t nv = ctr->n_valid;
+  const uint32_t nv = ctr->sort.n_valid;
   const uint32_t num_slices = (nv + kEmitTile - 1) / kEmitTile;
   const unsigned long long d_all = ctr->n_inst;
   if (d_all > cap_inst) {  // instance buffer too small: the host regrows it and re-runs the frame

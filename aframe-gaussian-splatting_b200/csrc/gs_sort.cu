@@ -36,8 +36,8 @@ struct DepthRange {
 };
 __device__ __forceinline__ DepthRange load_depth_range(const FrameCounters *ctr) {
   // min is stored bit-inverted so that a zero-initialised word means "no value yet"
-  const double mn = dec_f64(~ctr->min_enc);
-  const double mx = dec_f64(ctr->max_enc);
+  const double mn = dec_f64(~ctr->sort.min_enc);
+  const double mx = dec_f64(ctr->sort.max_enc);
   DepthRange r;
   r.min_depth = mn;
   r.depth_inv = __ddiv_rn(65535.0, __dsub_rn(mx, mn));  // index.js:558
@@ -108,9 +108,9 @@ __global__ void __launch_bounds__(256) k_depth_cull(const float4 *__restrict__ c
       cnt += s_cnt[k];
     }
     if (cnt) {
-      atomicMax(&ctr->min_enc, ~enc_f64(dmin));
-      atomicMax(&ctr->max_enc, enc_f64(dmax));
-      atomicAdd(&ctr->n_valid, cnt);
+      atomicMax(&ctr->sort.min_enc, ~enc_f64(dmin));
+      atomicMax(&ctr->sort.max_enc, enc_f64(dmax));
+      atomicAdd(&ctr->sort.n_valid, cnt);
     }
   }
 }
@@ -149,8 +149,8 @@ struct RadixArgs {
 template <int PASS>
 __device__ __forceinline__ uint32_t pass_n(const RadixArgs &a) {
   const FrameCounters *ctr = a.ctr;
-  if (PASS == PASS_D1) return ctr->n_valid ? a.n_host : 0u;
-  if (PASS == PASS_D2) return ctr->n_inrange;
+  if (PASS == PASS_D1) return ctr->sort.n_valid ? a.n_host : 0u;
+  if (PASS == PASS_D2) return ctr->sort.n_inrange;
   if (PASS == PASS_T1) return ctr->overflow ? 0u : (uint32_t)ctr->n_inst;
   return ctr->overflow ? 0u : ctr->n_inst_kept;
 }
@@ -195,7 +195,7 @@ __global__ void __launch_bounds__(kRadixThreads) k_radix_hist(RadixArgs a) {
   if (PASS == PASS_D1 && n) dr = load_depth_range(ctr);
   if (PASS == PASS_D2) {
     // quirk Q5: the reference's output keeps length validCount; slots never written stay 0
-    const uint32_t nv = ctr->n_valid;
+    const uint32_t nv = ctr->sort.n_valid;
     for (uint32_t j = n + blockIdx.x * blockDim.x + tid; j < nv; j += gridDim.x * blockDim.x) a.order[j] = 0u;
   }
   if (tid == 0) { s_in = 0; s_drop = 0; }
@@ -226,8 +226,8 @@ __global__ void __launch_bounds__(kRadixThreads) k_radix_hist(RadixArgs a) {
     if (lane == 0) { if (in) atomicAdd(&s_in, in); if (drop) atomicAdd(&s_drop, drop); }
     __syncthreads();
     if (tid == 0) {
-      if (s_in) atomicAdd(&ctr->n_inrange, s_in);
-      if (s_drop) atomicAdd(&ctr->n_dropped, s_drop);
+      if (s_in) atomicAdd(&ctr->sort.n_inrange, s_in);
+      if (s_drop) atomicAdd(&ctr->sort.n_dropped, s_drop);
     }
   }
 }

@@ -78,7 +78,7 @@ typedef struct gs_stats {
                               passes on a second stream: overlaps ms_sort)                    */
   float ms_bin;            /* instance emission + two tile-radix passes                      */
   float ms_raster;         /* tile raster + composite                                        */
-  float ms_total;          /* first kernel to last kernel of this frame on the device; with two
+  float ms_total;          /* first kernel to last kernel of this frame on the device; with several
                               frames in flight it includes waiting behind the previous raster  */
   uint32_t kernel_launches;/* kernels launched by the call                                   */
   uint32_t n_instances_kept;/* D  tile instances whose tile really meets the r<=2 footprint    */
@@ -153,12 +153,19 @@ typedef struct gs_render_params {
 GS_API int gs_render(gs_context *ctx, const gs_render_params *params, void *out_rgba, gs_stats *stats);
 
 /*
- * Pipelined form of gs_render (= gs_render_async + gs_wait).  gs_render_async enqueues the frame (one CUDA graph
- * launch on the context's stream; the RGBA frame and the counters are then copied to the host on a second stream)
- * and returns a ticket at once; gs_wait blocks until that frame is in out_rgba.  Two frames may be in flight, so
- * the device renders frame k+1 while frame k crosses PCIe (the reference likewise overlaps its worker sort with
- * drawing, index.js:206,439-440).  out_rgba must stay valid until gs_wait; use page-locked memory (gs_host_alloc)
- * for a truly asynchronous copy.  A third gs_render_async waits for the oldest frame first.
+ * Pipelined form of gs_render (= gs_render_async + gs_wait).  A frame is three stages on three internal streams,
+ * each one CUDA graph: A depth sort + projection, B tile binning, C raster; its counters and (for a host out_rgba)
+ * its RGBA frame are then copied to the host on a fourth stream.  gs_render_async enqueues all of that and returns
+ * a ticket at once; gs_wait blocks until that frame is in out_rgba.  THREE frames may be in flight (slot =
+ * ticket % 3): frame k is rasterised while frame k+1 is binned and frame k+2 sorted, and frame k-1 crosses PCIe
+ * (the reference likewise overlaps its worker sort with drawing, index.js:206,439-440).  A FOURTH
+ * gs_render_async first waits for the oldest frame.
+ * Buffer lifetime: out_rgba (and any device buffer passed with GS_RENDER_OUT_DEVICE / _TILED) must stay valid and
+ * untouched until gs_wait of that ticket returns, i.e. across up to three outstanding frames; use page-locked
+ * memory (gs_host_alloc) for a truly asynchronous copy.
+ * gs_wait(ticket) on a ticket that was already retired (by an earlier gs_wait, or implicitly when its slot was
+ * reused or the pipeline was drained by gs_clear / gs_sort / a growing push) returns GS_OK with the stats of the
+ * MOST RECENTLY completed frame, not necessarily that ticket's: the frame itself is already in out_rgba.
  */
 GS_API int gs_render_async(gs_context *ctx, const gs_render_params *params, void *out_rgba, uint64_t *out_ticket);
 GS_API int gs_wait(gs_context *ctx, uint64_t ticket, gs_stats *stats);

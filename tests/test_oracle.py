@@ -240,3 +240,50 @@ def test_golden_vectors(gs, orc):
     assert np.array_equal(o, g2["order"])
     img, _ = orc.render(cs, cc, o, g2["proj"], g2["modelview"], int(g2["width"]), int(g2["height"]), float(g2["focal"]))
     assert np.abs(img - g2["frame"].astype(np.float32)).max() <= 2e-3  # frame stored as float16
+
+
+def test_gl_coverage_check_agrees_with_affine_form(gs, orc):
+    """Independent check of the coverage definition: GL interpolates vPosition barycentrically over the two triangles
+    of the quad (index.js:52-62,158); the rasters use the affine form d.a2 / d.a1.  Evaluated without a1/a2 (vertex
+    positions as the shader emits them in fp32, barycentrics in fp64), the keep/discard decision may differ only on a
+    vanishing share of boundary pairs and the Gaussian weight of common pairs only at fp32 rounding level."""
+    rows, cs, cc, m, fr = scene_inputs(gs, orc, 20000, 0x5EED0001, 256, 144)
+    order = orc.sort(m, fr.view)
+    cov = orc.coverage_check(cs, cc, order, fr.proj, fr.modelview, 256, 144, fr.focal, nthreads=4)
+    _, st = orc.render(cs, cc, order, fr.proj, fr.modelview, 256, 144, fr.focal, nthreads=4)
+    assert cov["pairs_affine"] == st["fragments"] > 100000
+    assert cov["pairs_in_quad"] > cov["pairs_affine"]
+    assert cov["pairs_differ"] <= max(3, 2e-5 * cov["pairs_affine"])
+    assert cov["max_dalpha_common"] <= 1e-4
+    assert cov["max_alpha_flipped"] <= np.exp(-4.0) + 1e-6  # a flipped pair sits on the r^2 = 4 boundary
+
+
+def test_depth_interop_oracle(gs, orc):
+    """depthTest:true / depthWrite:false (index.js:179-180): fragments behind foreign geometry are rejected, LEQUAL."""
+    rows, cs, cc, m, fr = scene_inputs(gs, orc, 5000, 77, 128, 72)
+    order = orc.sort(m, fr.view)
+    args = (cs, cc, order, fr.proj, fr.modelview, 128, 72, fr.focal)
+    base, st0 = orc.render(*args, bg=(0.2, 0.3, 0.4, 1.0), nthreads=2)
+    far, _ = orc.render(*args, bg=(0.2, 0.3, 0.4, 1.0), nthreads=2, depth_in=np.ones((72, 128), np.float32))
+    assert np.array_equal(base, far)  # every splat in front of the far plane passes (z/w <= 1 after the clip)
+    near, st1 = orc.render(*args, bg=(0.2, 0.3, 0.4, 1.0), nthreads=2, depth_in=np.zeros((72, 128), np.float32))
+    assert st1["fragments"] == 0 and np.allclose(near, [0.2, 0.3, 0.4, 1.0])
+    p = orc.project(cs, cc, order, fr.proj, fr.modelview, 128, 72, fr.focal)
+    zw = (p["zndc"][p["visible"] == 1] * np.float32(0.5) + np.float32(0.5)).astype(np.float32)
+    cut = np.float32(np.median(zw))
+    half = np.full((72, 128), cut, np.float32)
+    half[:, 64:] = 1.0
+    mid, st2 = orc.render(*args, bg=(0.2, 0.3, 0.4, 1.0), nthreads=2, depth_in=half)
+    assert 0 < st2["fragments"] < st0["fragments"]
+    assert np.array_equal(mid[:, 64:], base[:, 64:]) and not np.array_equal(mid[:, :64], base[:, :64])
+    # LEQUAL: a splat exactly at the stored depth passes, one ulp behind fails
+    for j in np.nonzero(p["visible"] == 1)[0]:
+        one = order[j:j + 1]
+        _, s1 = orc.render(cs, cc, one, fr.proj, fr.modelview, 128, 72, fr.focal, nthreads=1)
+        if s1["fragments"] > 0:
+            break
+    z = np.float32(p["zndc"][j] * np.float32(0.5) + np.float32(0.5))
+    a, sa = orc.render(cs, cc, one, fr.proj, fr.modelview, 128, 72, fr.focal, nthreads=1, depth_in=np.full((72, 128), z, np.float32))
+    b, sb = orc.render(cs, cc, one, fr.proj, fr.modelview, 128, 72, fr.focal, nthreads=1,
+                       depth_in=np.full((72, 128), np.nextafter(z, np.float32(0)), np.float32))
+    assert sa["fragments"] == s1["fragments"] > 0 and sb["fragments"] == 0
