@@ -9,7 +9,8 @@ host-side mirror of the reference's component interface, and the synthetic scene
 """
 from . import _lib, build, dist, ply, scenes, three_math  # noqa: F401
 from ._lib import (GS_FORMAT_RGBA8, GS_FORMAT_RGBA32F, GS_RENDER_OUT_DEVICE, GS_RENDER_OUT_PEER,  # noqa: F401
-                   GS_RENDER_OUT_TILED, GS_RENDER_REUSE_SORT, GsRenderParams, GsStats)
+                   GS_RENDER_OUT_TILED, GS_RENDER_REUSE_SORT, GS_RENDER_STATS, GS_RENDER_DEPTH_DEVICE, GsRenderParams,
+                   GsStats)
 from .renderer import GsError, SplatContext  # noqa: F401
 from .scenes import FrameInputs, make_frame, synth_splats  # noqa: F401
 from .component import GaussianSplattingComponent, SortWorker  # noqa: F401

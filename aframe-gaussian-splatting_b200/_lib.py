@@ -11,6 +11,7 @@ LIB_PATH = os.path.join(HERE, "libgsplat_b200.so")
 GS_OK, GS_ERR_INVALID, GS_ERR_CUDA, GS_ERR_OOM, GS_ERR_CAPACITY, GS_ERR_EMPTY = 0, -1, -2, -3, -4, -5
 GS_FORMAT_RGBA8, GS_FORMAT_RGBA32F = 0, 1
 GS_RENDER_OUT_DEVICE, GS_RENDER_REUSE_SORT, GS_RENDER_OUT_TILED, GS_RENDER_OUT_PEER = 1, 2, 4, 8
+GS_RENDER_STATS, GS_RENDER_DEPTH_DEVICE = 16, 32
 
 
 class GsStats(C.Structure):
@@ -20,6 +21,8 @@ class GsStats(C.Structure):
         ("min_depth", C.c_double), ("max_depth", C.c_double),
         ("ms_sort", C.c_float), ("ms_project", C.c_float), ("ms_bin", C.c_float), ("ms_raster", C.c_float),
         ("ms_total", C.c_float), ("kernel_launches", C.c_uint32), ("n_instances_kept", C.c_uint32),
+        ("n_tile_instances", C.c_uint64), ("n_records_streamed", C.c_uint64), ("n_pair_tests", C.c_uint64),
+        ("n_pair_hits", C.c_uint64),
     ]
 
     def as_dict(self):
@@ -31,7 +34,7 @@ class GsRenderParams(C.Structure):
         ("proj", C.c_float * 16), ("modelview", C.c_float * 16),
         ("width", C.c_uint32), ("height", C.c_uint32), ("focal", C.c_float),
         ("bg_rgba", C.c_float * 4), ("has_cutout", C.c_int32), ("cutout16", C.c_float * 16),
-        ("out_format", C.c_int32), ("flags", C.c_uint32),
+        ("out_format", C.c_int32), ("flags", C.c_uint32), ("depth_in", C.c_void_p),
     ]
 
 

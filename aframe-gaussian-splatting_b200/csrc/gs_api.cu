@@ -121,12 +121,23 @@ static int ensure_instances(gs_context *c, uint64_t need) {
   return GS_OK;
 }
 
-static int ensure_tiles(gs_context *c, uint32_t n_tiles) {
-  if (n_tiles <= c->tiles_cap && c->tile_range[0]) return GS_OK;
-  dev_free(c->tile_range[0]); dev_free(c->tile_range[1]);
-  GS_CUDA(c, dev_alloc(&c->tile_range[0], (size_t)n_tiles + 1));
-  GS_CUDA(c, dev_alloc(&c->tile_range[1], (size_t)n_tiles + 1));
-  c->tiles_cap = n_tiles;
+static int ensure_bins(gs_context *c, uint32_t n_bins) {
+  if (n_bins <= c->bins_cap && c->bin_range[0]) return GS_OK;
+  dev_free(c->bin_range[0]); dev_free(c->bin_range[1]);
+  GS_CUDA(c, dev_alloc(&c->bin_range[0], (size_t)n_bins + 1));
+  GS_CUDA(c, dev_alloc(&c->bin_range[1], (size_t)n_bins + 1));
+  c->bins_cap = n_bins;
+  return GS_OK;
+}
+
+static int ensure_tile_stats(gs_context *c, uint32_t n_tiles) {
+  if (n_tiles <= c->tile_stats_cap && c->tile_stats) return GS_OK;
+  dev_free(c->tile_stats);
+  if (c->tile_stats_host) cudaFreeHost(c->tile_stats_host);
+  c->tile_stats_host = nullptr;
+  GS_CUDA(c, dev_alloc(&c->tile_stats, (size_t)n_tiles));
+  GS_CUDA(c, cudaHostAlloc((void **)&c->tile_stats_host, sizeof(uint4) * (size_t)n_tiles, cudaHostAllocDefault));
+  c->tile_stats_cap = n_tiles;
   return GS_OK;
 }
 
@@ -219,6 +230,10 @@ extern "C" int gs_create(int device_ordinal, gs_context **out_ctx) {
   }
   if ((e = cudaMalloc((void **)&c->sort_hdr, sizeof(SortHeader))) != cudaSuccess) return bail("cudaMalloc", e);
   c->use_graphs = getenv("GS_NO_GRAPH") == nullptr;
+  {  // pixel loop of the raster: packed fp32x2 (default) or scalar (GS_RASTER=scalar); both give identical frames
+    const char *rk = getenv("GS_RASTER");
+    c->raster_base_flags = (rk && strcmp(rk, "scalar") == 0) ? 0u : 1u;
+  }
   // parseInt quirk table (gs_pack.cu): strtod("<d>e-<k>") for k = 323..7, d = 1..9, ascending
   std::vector<double> tab;
   for (int k = 323; k >= 7; --k)
@@ -247,7 +262,8 @@ extern "C" int gs_destroy(gs_context *c) {
   for (int i = 0; i < 2; ++i) { dev_free(c->order[i]); dev_free(c->proj_rec[i]); dev_free(c->rect[i]); }
   dev_free(c->inst_tile); dev_free(c->inst_idx); dev_free(c->inst_tile_b); dev_free(c->inst_tile_f); dev_free(c->inst_idx_b);
   dev_free(c->inst_rec[0]); dev_free(c->inst_rec[1]);
-  dev_free(c->tile_range[0]); dev_free(c->tile_range[1]); dev_free(c->quirk_table);
+  dev_free(c->bin_range[0]); dev_free(c->bin_range[1]); dev_free(c->quirk_table); dev_free(c->tile_stats);
+  if (c->tile_stats_host) cudaFreeHost(c->tile_stats_host);
   if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
   drop_graphs(c);
   for (uint32_t r = 0; r < c->peer_world; ++r)
@@ -258,6 +274,7 @@ extern "C" int gs_destroy(gs_context *c) {
   for (auto &sl : c->slot) {
     dev_free(sl.ctr); dev_free(sl.fp);
     if (sl.frame_dev) cudaFree(sl.frame_dev);
+    if (sl.depth_dev) cudaFree(sl.depth_dev);
     if (sl.ctr_host) cudaFreeHost(sl.ctr_host);
     if (sl.fp_host) cudaFreeHost(sl.fp_host);
     for (auto &ev : sl.ev) if (ev) cudaEventDestroy(ev);
@@ -395,7 +412,7 @@ extern "C" int gs_sort(gs_context *c, const float view[4], const float *cutout16
   GS_CUDA(c, cudaStreamSynchronize(c->rstream));
   gs_context::Slot &sl = c->slot[0];
   c->last_set = 0;
-  const FrameBufs bufs{c->order[0], c->proj_rec[0], c->rect[0], c->inst_rec[0], c->tile_range[0]};
+  const FrameBufs bufs{c->order[0], c->proj_rec[0], c->rect[0], c->inst_rec[0], c->bin_range[0]};
   memset(sl.fp_host, 0, sizeof(FrameParams));
   fill_sort_consts(sl.fp_host->sc, view, cutout16_or_null);
   GS_CUDA(c, cudaMemcpyAsync(sl.fp, sl.fp_host, sizeof(FrameParams), cudaMemcpyHostToDevice, c->stream));
@@ -439,7 +456,7 @@ extern "C" uint32_t gs_owned_tiles(uint32_t width, uint32_t height, uint32_t ran
 }
 
 static FrameBufs slot_bufs(gs_context *c, const gs_context::Slot &sl) {
-  return FrameBufs{c->order[sl.set], c->proj_rec[sl.set], c->rect[sl.set], c->inst_rec[sl.set], c->tile_range[sl.set]};
+  return FrameBufs{c->order[sl.set], c->proj_rec[sl.set], c->rect[sl.set], c->inst_rec[sl.set], c->bin_range[sl.set]};
 }
 
 // Stage A of a frame (sort stream): per-frame inputs to the device, depth sort, vertex shader.  All per-frame
@@ -476,14 +493,14 @@ static cudaError_t enqueue_sort_stage(gs_context *c, gs_context::Slot &sl, bool 
 }
 
 // Stage B (bin stream): tile instances in draw order, stable sort by tile, per-tile record lists and ranges.
-static cudaError_t enqueue_bin_stage(gs_context *c, gs_context::Slot &sl, uint32_t n_tiles, bool external_events) {
+static cudaError_t enqueue_bin_stage(gs_context *c, gs_context::Slot &sl, uint32_t n_bins, bool external_events) {
   auto rec = [&](cudaEvent_t ev, cudaStream_t st) {
     return external_events ? cudaEventRecordWithFlags(ev, st, cudaEventRecordExternal) : cudaEventRecord(ev, st);
   };
   cudaStream_t m = c->bstream;
   const FrameBufs b = slot_bufs(c, sl);
   cudaError_t e;
-  if ((e = cudaMemsetAsync(b.tile_range, 0, sizeof(uint2) * (size_t)n_tiles, m))) return e;
+  if ((e = cudaMemsetAsync(b.bin_range, 0, sizeof(uint2) * (size_t)n_bins, m))) return e;
   if ((e = rec(sl.ev[2], m))) return e;
   launch_emit(c, sl.fp, sl.ctr, b, m);   // 2 launches (k_emit also histograms pass T1)
   launch_tile_radix(c, sl.ctr, b, m);    // 5 launches
@@ -492,7 +509,7 @@ static cudaError_t enqueue_bin_stage(gs_context *c, gs_context::Slot &sl, uint32
   return cudaGetLastError();
 }
 
-// Stage C (raster stream, low priority): reads only this frame's inst_rec / tile_range copy.
+// Stage C (raster stream, low priority): reads only this frame's inst_rec / bin_range copy.
 static cudaError_t enqueue_raster_stage(gs_context *c, gs_context::Slot &sl, uint32_t n_tiles, bool external_events) {
   auto rec = [&](cudaEvent_t ev, cudaStream_t st) {
     return external_events ? cudaEventRecordWithFlags(ev, st, cudaEventRecordExternal) : cudaEventRecord(ev, st);
@@ -500,7 +517,7 @@ static cudaError_t enqueue_raster_stage(gs_context *c, gs_context::Slot &sl, uin
   cudaError_t e;
   if (sl.peer) launch_peer_acquire(c, sl.fp, sl.ctr, c->rstream);
   if ((e = rec(sl.ev_r0, c->rstream))) return e;
-  launch_raster(c, sl.fp, n_tiles, slot_bufs(c, sl), c->rstream);
+  launch_raster(c, sl.fp, n_tiles, slot_bufs(c, sl), sl.raster_flags, c->rstream);
   if ((e = rec(sl.ev[4], c->rstream))) return e;
   if (sl.peer) launch_peer_signal_wait(c, sl.fp, sl.ctr, c->rstream);
   return cudaGetLastError();
@@ -536,7 +553,7 @@ static int run_graph(gs_context *c, cudaGraphExec_t &ge, cudaStream_t stream, F 
 // Three frames overlap: while frame k is rasterised (stream C), frame k+1 is binned (stream B) and frame k+2 is
 // sorted / projected (stream A).  A and B are high priority: their short latency-bound kernels slot in as the
 // long issue-bound raster's CTAs retire.  Stage hand-offs are events; buffers between stages are double-buffered.
-static int launch_frame(gs_context *c, gs_context::Slot &sl, bool reuse, uint32_t n_tiles) {
+static int launch_frame(gs_context *c, gs_context::Slot &sl, bool reuse, uint32_t n_tiles, uint32_t n_bins) {
   // (re)capture when anything baked into the launches changed
   gs_context::GraphKey k;
   k.n = c->n; k.n_tiles = n_tiles; k.cap_inst = c->cap_inst; k.p0 = c->depth; k.p1 = c->inst_rec[0]; k.p2 = c->center_scale;
@@ -553,13 +570,18 @@ static int launch_frame(gs_context *c, gs_context::Slot &sl, bool reuse, uint32_
   // B: needs A of this frame; inst_rec/tile_range[set] must no longer be read by the raster that used them last
   GS_CUDA(c, cudaStreamWaitEvent(c->bstream, sl.ev_sorted, 0));
   if (c->bin_set_free[set]) GS_CUDA(c, cudaStreamWaitEvent(c->bstream, c->bin_set_free[set], 0));
-  if ((rc = run_graph(c, sl.graph_b[set], c->bstream, [&](bool ext) { return enqueue_bin_stage(c, sl, n_tiles, ext); }))) return rc;
+  if ((rc = run_graph(c, sl.graph_b[set], c->bstream, [&](bool ext) { return enqueue_bin_stage(c, sl, n_bins, ext); }))) return rc;
   GS_CUDA(c, cudaEventRecord(sl.ev_binned, c->bstream));
   c->sort_set_free[set] = sl.ev_binned;
   // C
   GS_CUDA(c, cudaStreamWaitEvent(c->rstream, sl.ev_binned, 0));
-  if ((rc = run_graph(c, sl.peer ? sl.graph_rp[set] : sl.graph_r[set], c->rstream,
-                      [&](bool ext) { return enqueue_raster_stage(c, sl, n_tiles, ext); }))) return rc;
+  if (sl.raster_flags == c->raster_base_flags) {
+    if ((rc = run_graph(c, sl.peer ? sl.graph_rp[set] : sl.graph_r[set], c->rstream,
+                        [&](bool ext) { return enqueue_raster_stage(c, sl, n_tiles, ext); }))) return rc;
+  } else {
+    // depth-tested / statistics frames use other instantiations of the raster: plain launches, no cached graph
+    GS_CUDA(c, enqueue_raster_stage(c, sl, n_tiles, false));
+  }
   sl.launches = (reuse ? 0u : 7u) + 1u + 8u + 1u;
   return GS_OK;
 }
@@ -573,6 +595,9 @@ static int enqueue_readback(gs_context *c, gs_context::Slot &sl) {
   GS_CUDA(c, cudaMemcpyAsync(sl.ctr_host, sl.ctr, sizeof(FrameCounters), cudaMemcpyDeviceToHost, c->copy_stream));
   if (sl.host_out)
     GS_CUDA(c, cudaMemcpyAsync(sl.out_user, sl.frame_src, sl.out_bytes, cudaMemcpyDeviceToHost, c->copy_stream));
+  if (sl.raster_flags & 4u)
+    GS_CUDA(c, cudaMemcpyAsync(c->tile_stats_host, c->tile_stats, sizeof(uint4) * (size_t)sl.fp_host->rc.n_tiles,
+                               cudaMemcpyDeviceToHost, c->copy_stream));
   GS_CUDA(c, cudaEventRecord(sl.ev_copied, c->copy_stream));
   return GS_OK;
 }
@@ -593,6 +618,9 @@ static int submit(gs_context *c, gs_context::Slot &sl) {
   rc.tiles_x = (p->width + kTile - 1) / kTile;
   rc.tiles_y = (p->height + kTile - 1) / kTile;
   rc.n_tiles = rc.tiles_x * rc.tiles_y;
+  rc.bins_x = (p->width + kBin - 1) / kBin;
+  rc.bins_y = (p->height + kBin - 1) / kBin;
+  rc.n_bins = rc.bins_x * rc.bins_y;
   memcpy(rc.bg, p->bg_rgba, sizeof(rc.bg));
   rc.shard_rank = c->shard_rank;
   rc.shard_world = c->shard_world;
@@ -639,11 +667,28 @@ static int submit(gs_context *c, gs_context::Slot &sl) {
     fp.out = sl.out_user;
     sl.frame_src = nullptr;
   }
+  // raster instantiation: pixel loop (packed fp32x2 by default), depth test, statistics
+  sl.raster_flags = c->raster_base_flags | (p->depth_in ? 2u : 0u) | ((p->flags & GS_RENDER_STATS) ? 4u : 0u);
+  if (p->depth_in) {
+    if (p->flags & GS_RENDER_DEPTH_DEVICE) {
+      fp.depth_in = p->depth_in;
+    } else {  // host depth buffer: staged per slot, copied on the sort stream (the raster stage is ordered after it)
+      const size_t bytes = sizeof(float) * (size_t)p->width * p->height;
+      if (bytes > sl.depth_bytes || !sl.depth_dev) {
+        if (sl.depth_dev) cudaFree(sl.depth_dev);
+        sl.depth_dev = nullptr;
+        GS_CUDA(c, cudaMalloc(&sl.depth_dev, bytes));
+        sl.depth_bytes = bytes;
+      }
+      GS_CUDA(c, cudaMemcpyAsync(sl.depth_dev, p->depth_in, bytes, cudaMemcpyHostToDevice, c->stream));
+      fp.depth_in = sl.depth_dev;
+    }
+  }
   const bool reuse = (p->flags & GS_RENDER_REUSE_SORT) && c->have_order;
   // a frame normally takes the buffer set the previous frame did not; a frame that reuses the last sort must read
   // that sort's set, so it runs in it
   sl.set = reuse ? c->last_set : (c->last_set ^ 1);
-  if ((rcode = launch_frame(c, sl, reuse, rc.n_tiles))) return rcode;
+  if ((rcode = launch_frame(c, sl, reuse, rc.n_tiles, rc.n_bins))) return rcode;
   if ((rcode = enqueue_readback(c, sl))) return rcode;
   c->last_set = sl.set;
   sl.pending = true;
@@ -699,6 +744,17 @@ static int wait_slot(gs_context *c, gs_context::Slot &sl, gs_stats *stats) {
   stats_from_counters(c, *sl.ctr_host);
   c->stats.kernel_launches = sl.launches;
   c->stats.n_tiles = sl.fp_host->rc.n_tiles;
+  if (sl.raster_flags & 4u) {  // GS_RENDER_STATS: per-tile {records streamed, records kept, pair tests, pair hits}
+    const RenderConsts &rc = sl.fp_host->rc;
+    for (uint32_t t = 0; t < rc.n_tiles; ++t) {
+      if (rc.shard_world > 1 && ((t % rc.tiles_x) / kTilesPerBin) % rc.shard_world != rc.shard_rank) continue;
+      const uint4 v = c->tile_stats_host[t];
+      c->stats.n_records_streamed += v.x;
+      c->stats.n_tile_instances += v.y;
+      c->stats.n_pair_tests += v.z;
+      c->stats.n_pair_hits += v.w;
+    }
+  }
   c->stats.width = sl.params.width;
   c->stats.height = sl.params.height;
   cudaEventElapsedTime(&c->stats.ms_sort, sl.ev[0], sl.ev[1]);
@@ -718,22 +774,24 @@ extern "C" int gs_render_async(gs_context *c, const gs_render_params *p, void *o
     return fail(c, GS_ERR_INVALID, "frame size must be within 1..4096 per side");
   if (p->out_format != GS_FORMAT_RGBA8 && p->out_format != GS_FORMAT_RGBA32F) return fail(c, GS_ERR_INVALID, "bad out_format");
   const uint32_t n_tiles = ((p->width + kTile - 1) / kTile) * ((p->height + kTile - 1) / kTile);
-  if (n_tiles >= 0xFFFFu) return fail(c, GS_ERR_INVALID, "more than 65534 tiles");
+  const uint32_t n_bins = ((p->width + kBin - 1) / kBin) * ((p->height + kBin - 1) / kBin);  // <= 64*64: fits the 16-bit bin id
   GS_CUDA(c, cudaSetDevice(c->device));
   const uint64_t ticket = c->next_ticket;
   gs_context::Slot &sl = c->slot[ticket % 3];
   int rcode;
   if (sl.pending && (rcode = wait_slot(c, sl, nullptr))) return rcode;  // slot reuse: its previous frame must be done
   if ((p->flags & GS_RENDER_REUSE_SORT) && c->have_order && (rcode = drain(c))) return rcode;  // runs in the last sort's buffers
+  if ((p->flags & GS_RENDER_STATS) && (rcode = drain(c))) return rcode;  // the per-tile statistics buffer is not double-buffered
   // growing any shared buffer needs an idle pipeline
-  const bool grow = !(c->scratch_cap >= c->cap && c->depth) || !(n_tiles <= c->tiles_cap && c->tile_range[0]) || c->cap_inst == 0;
+  const bool grow = !(c->scratch_cap >= c->cap && c->depth) || !(n_bins <= c->bins_cap && c->bin_range[0]) || !(n_tiles <= c->tile_stats_cap && c->tile_stats) || c->cap_inst == 0;
   if (grow) {
     if ((rcode = drain(c))) return rcode;
     GS_CUDA(c, cudaStreamSynchronize(c->stream));
     GS_CUDA(c, cudaStreamSynchronize(c->bstream));
     GS_CUDA(c, cudaStreamSynchronize(c->rstream));
     if ((rcode = ensure_scratch(c))) return rcode;
-    if ((rcode = ensure_tiles(c, n_tiles))) return rcode;
+    if ((rcode = ensure_bins(c, n_bins))) return rcode;
+    if ((rcode = ensure_tile_stats(c, n_tiles))) return rcode;
     if (c->cap_inst == 0 && (rcode = ensure_instances(c, std::max<uint64_t>(1u << 20, (uint64_t)c->n * 4)))) return rcode;
   }
   sl.params = *p;

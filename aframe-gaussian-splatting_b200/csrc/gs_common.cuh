@@ -17,7 +17,13 @@
 
 namespace gs {
 
-constexpr int kTile = 16;                 // 16x16 screen tiles (north_star)
+constexpr int kTile = 16;                 // 16x16 screen tiles (north_star): one raster CTA per tile
+// Binning granularity: splats are binned to 64x64-pixel BINS (4x4 tiles), not to tiles.  A splat meets ~4x fewer bins
+// than tiles, so the instance emission and the stable sort by bin id handle ~4x fewer elements; each tile's raster CTA
+// streams its bin's list and culls it against its own 16x16 pixels on the fly (exact footprint test, lane-parallel).
+constexpr int kBinShift = 6;
+constexpr int kBin = 1 << kBinShift;      // 64 pixels
+constexpr int kTilesPerBin = kBin / kTile;  // 4 tile columns / rows per bin
 constexpr int kRadixThreads = 256;
 constexpr int kRadixItems = 16;
 constexpr int kRadixTile = kRadixThreads * kRadixItems;  // 4096 elements per look-back tile
@@ -60,6 +66,7 @@ struct RenderConsts {
   float vw, vh, focal;
   uint32_t width, height;
   uint32_t tiles_x, tiles_y, n_tiles;
+  uint32_t bins_x, bins_y, n_bins;
   float bg[4];
   uint32_t shard_rank, shard_world;
   int32_t out_format;
@@ -80,6 +87,7 @@ struct FrameParams {
   SortConsts sc;
   RenderConsts rc;
   void *out;  // frame (or packed owned tiles) destination of the raster
+  const void *depth_in;  // optional window-space depth of foreign geometry (f32, width*height, row 0 = bottom)
   // ---- fused raster + exchange over NVLink peer memory (GS_RENDER_OUT_PEER) ----
   uint32_t n_peer;                       // 0: plain output; else every finished tile is stored into all ranks' frames
   uint32_t peer_rank;
@@ -138,8 +146,11 @@ struct gs_context {
   uint32_t table_d_stride = 0;
 
   // ---- per-frame tables ----
-  uint32_t tiles_cap = 0;
-  uint2 *tile_range[2] = {nullptr, nullptr};  // [T] {start, end} into inst_rec, one per slot (read by the raster)
+  uint32_t bins_cap = 0;
+  uint2 *bin_range[2] = {nullptr, nullptr};  // [bins] {start, end} into inst_rec, one per slot (read by the raster)
+  uint4 *tile_stats = nullptr;     // [tiles] per-tile counts of a GS_RENDER_STATS frame
+  uint4 *tile_stats_host = nullptr;  // pinned copy
+  uint32_t tile_stats_cap = 0;
   double *quirk_table = nullptr;   // parseInt quirk thresholds (device)
   int quirk_n = 0;
   gs::SortHeader *sort_hdr = nullptr;  // device: counters header of the last sort (for GS_RENDER_REUSE_SORT)
@@ -152,6 +163,9 @@ struct gs_context {
     gs::FrameParams *fp_host = nullptr;      // pinned staging
     void *frame_dev = nullptr;               // used when the caller's buffer is host memory
     size_t frame_bytes = 0;
+    void *depth_dev = nullptr;               // staging of a host depth_in
+    size_t depth_bytes = 0;
+    uint32_t raster_flags = 0;               // k_raster instantiation of this frame (packed | depth | stats)
     cudaEvent_t ev[5]{};                     // stage boundaries (timing)
     cudaEvent_t evp[2]{};                    // k_project on the aux stream (timing)
     cudaEvent_t ev_done = nullptr, ev_copied = nullptr;
@@ -187,6 +201,7 @@ struct gs_context {
   cudaStream_t aux_stream = nullptr;             // runs k_project beside the depth radix passes
   cudaEvent_t ev_fork[2]{}, ev_join[2]{};
   bool use_graphs = true;
+  uint32_t raster_base_flags = 1;                // default pixel loop: 1 = packed fp32x2, 0 = scalar
   // graph cache key: anything baked into the captured launches
   struct GraphKey { uint32_t n = 0, n_tiles = 0; uint64_t cap_inst = 0; const void *p0 = nullptr, *p1 = nullptr, *p2 = nullptr; } gkey;
 
@@ -218,7 +233,7 @@ struct FrameBufs {
   float4 *proj_rec;
   uint32_t *rect;
   float4 *inst_rec;
-  uint2 *tile_range;
+  uint2 *bin_range;  // [n_bins] {start, end} of each bin's run in inst_rec
 };
 
 // -- launchers (each .cu file owns its kernels); every per-frame input comes from device memory (fp, ctr) --
@@ -229,7 +244,7 @@ void launch_project(gs_context *c, const FrameParams *fp, const FrameBufs &b, cu
 void launch_emit(gs_context *c, const FrameParams *fp, FrameCounters *ctr, const FrameBufs &b, cudaStream_t st);  // 2 launches
 void launch_tile_radix(gs_context *c, FrameCounters *ctr, const FrameBufs &b, cudaStream_t st);  // 5 launches
 void launch_tile_ranges(gs_context *c, FrameCounters *ctr, const FrameBufs &b, cudaStream_t st);
-void launch_raster(gs_context *c, const FrameParams *fp, uint32_t n_tiles, const FrameBufs &b, cudaStream_t st);
+void launch_raster(gs_context *c, const FrameParams *fp, uint32_t n_tiles, const FrameBufs &b, uint32_t flags, cudaStream_t st);
 void launch_peer_acquire(gs_context *c, const FrameParams *fp, FrameCounters *ctr, cudaStream_t st);
 void launch_peer_signal_wait(gs_context *c, const FrameParams *fp, FrameCounters *ctr, cudaStream_t st);
 struct PeerRows { unsigned long long *p[kMaxPeers]; };
@@ -259,20 +274,59 @@ __host__ __device__ inline double dec_f64(unsigned long long e) {
 #endif
 }
 
-// ---- multi-GPU tile ownership: rank r owns the tile COLUMNS tx with tx % world == r (16-pixel wide vertical
-// stripes, interleaved), so the owned tiles of any tile rectangle have a closed form ----
-__host__ __device__ inline uint32_t owned_cols(uint32_t tiles_x, uint32_t rank, uint32_t world) {
-  return rank < tiles_x ? (tiles_x - 1 - rank) / world + 1 : 0u;
+// Exact footprint-vs-box test shared by the bin emission (64x64 box) and the raster's cull (16x16 box).
+// The box holds pixel CENTRES [x0, x0 + extent] x [y0, y0 + extent]; the footprint is the set r^2 = px^2 + py^2 <= 4 with
+// (px, py) = (d.a2, d.a1), d = sample - centre (index.js:158-172).  r^2 is a convex quadratic of d, so when the centre
+// lies outside the box its minimum over the box is attained on the edge(s) facing the centre; the test evaluates those
+// minima in plain fp32 and keeps a 0.5 % slack (4.02) so that it can only err on the side of keeping the splat.
+__device__ __forceinline__ bool footprint_meets_box(float cx, float cy, float a1x, float a1y, float a2x, float a2y, float x0,
+                                                    float y0, float extent) {
+  const float xa = x0 - cx, xb = xa + extent;
+  const float ya = y0 - cy, yb = ya + extent;
+  const bool in_x = (xa <= 0.0f) && (xb >= 0.0f), in_y = (ya <= 0.0f) && (yb >= 0.0f);
+  if (in_x && in_y) return true;
+  // q(d) = |(a2.d, a1.d)|^2 = M00 dx^2 + 2 M01 dx dy + M11 dy^2: edge minimisers need M01/M11, M01/M00
+  const float cross = a2x * a2y + a1x * a1y;
+  float qmin = 3.0e38f;
+  if (!in_x) {  // nearest vertical edge, minimise over y on it; (px,py) evaluated at the found point
+    const float dx = (xa > 0.0f) ? xa : xb;
+    const float inv_yy = __fdividef(1.0f, a2y * a2y + a1y * a1y);
+    const float t = fminf(fmaxf(-dx * cross * inv_yy, ya), yb);
+    const float px = dx * a2x + t * a2y, py = dx * a1x + t * a1y;
+    qmin = px * px + py * py;
+  }
+  if (!in_y) {  // nearest horizontal edge, minimise over x on it
+    const float dy = (ya > 0.0f) ? ya : yb;
+    const float inv_xx = __fdividef(1.0f, a2x * a2x + a1x * a1x);
+    const float t = fminf(fmaxf(-dy * cross * inv_xx, xa), xb);
+    const float px = t * a2x + dy * a2y, py = t * a1x + dy * a1y;
+    qmin = fminf(qmin, px * px + py * py);
+  }
+  return !(qmin > 4.02f);  // NaN keeps
 }
-// packed index of owned tile (tx, ty) in rank's tile buffer (row-major over its own columns)
-__host__ __device__ inline uint32_t owned_slot(uint32_t tx, uint32_t ty, uint32_t tiles_x, uint32_t rank, uint32_t world) {
-  return ty * owned_cols(tiles_x, rank, world) + (tx - rank) / world;
+
+// ---- multi-GPU ownership: rank r owns the BIN COLUMNS bx with bx % world == r (64-pixel wide vertical stripes,
+// interleaved), so the owned bins of any bin rectangle have a closed form; a tile belongs to the owner of its bin ----
+__host__ __device__ inline uint32_t owned_cols(uint32_t bins_x, uint32_t rank, uint32_t world) {
+  return rank < bins_x ? (bins_x - 1 - rank) / world + 1 : 0u;
 }
-// first owned column >= tx0 and number of owned columns in [tx0, tx1]
-__host__ __device__ inline void owned_span(uint32_t tx0, uint32_t tx1, uint32_t rank, uint32_t world, uint32_t &first,
+// first owned bin column >= bx0 and number of owned columns in [bx0, bx1]
+__host__ __device__ inline void owned_span(uint32_t bx0, uint32_t bx1, uint32_t rank, uint32_t world, uint32_t &first,
                                            uint32_t &ncols) {
-  first = tx0 + (rank + world - tx0 % world) % world;
-  ncols = first <= tx1 ? (tx1 - first) / world + 1 : 0u;
+  first = bx0 + (rank + world - bx0 % world) % world;
+  ncols = first <= bx1 ? (bx1 - first) / world + 1 : 0u;
+}
+// owned TILE columns of a rank: 4 per owned bin column, except that the last bin column may hold fewer tiles
+__host__ __device__ inline uint32_t owned_tile_cols(uint32_t tiles_x, uint32_t rank, uint32_t world) {
+  const uint32_t full = tiles_x / kTilesPerBin, rem = tiles_x % kTilesPerBin;
+  uint32_t n = kTilesPerBin * owned_cols(full, rank, world);
+  if (rem && full % world == rank) n += rem;
+  return n;
+}
+// packed index of owned tile (tx, ty) in rank's tile buffer (row-major over its own tile columns)
+__host__ __device__ inline uint32_t owned_slot(uint32_t tx, uint32_t ty, uint32_t tiles_x, uint32_t rank, uint32_t world) {
+  const uint32_t bx = tx / kTilesPerBin;
+  return ty * owned_tile_cols(tiles_x, rank, world) + (bx - rank) / world * kTilesPerBin + (tx % kTilesPerBin);
 }
 
 }  // namespace gs

@@ -1,5 +1,5 @@
 // gs_project.cu — per-splat projection (the reference's vertex shader, index.js:101-164) and the
-// ordered emission of 16x16 tile instances.
+// ordered emission of bin instances (64x64-pixel bins = 4x4 raster tiles; "tile" below means bin).
 //
 //   k_project  : fp32 restatement of the vertex shader, op for op (no FMA contraction), producing a
 //                32 B projected record per splat + its packed tile rectangle.
@@ -128,13 +128,14 @@ __global__ void __launch_bounds__(256) k_project(const float4 *__restrict__ cs, 
           fx1 = fminf(fx1, (float)rc.width - 1.0f);
           fy1 = fminf(fy1, (float)rc.height - 1.0f);
           if (fx0 <= fx1 && fy0 <= fy1) {
-            const uint32_t tx0 = (uint32_t)fx0 >> 4, tx1 = (uint32_t)fx1 >> 4;
-            const uint32_t ty0 = (uint32_t)fy0 >> 4, ty1 = (uint32_t)fy1 >> 4;
+            // rectangle of 64x64-pixel BINS (at most 64 per axis for frames up to 4096 px: never equals kNoRect)
+            const uint32_t tx0 = (uint32_t)fx0 >> kBinShift, tx1 = (uint32_t)fx1 >> kBinShift;
+            const uint32_t ty0 = (uint32_t)fy0 >> kBinShift, ty1 = (uint32_t)fy1 >> kBinShift;
             rect = tx0 | (tx1 << 8) | (ty0 << 16) | (ty1 << 24);
-            // alpha as f32 = float(byte)/255.0 (index.js:156); rgb stay packed, converted in the raster
-            const float alpha = DIV((float)(q.w >> 24), 255.0f);
+            // rgba stay packed (converted to float(byte)/255.0, index.js:152-157, once per record in the raster);
+            // the last slot carries gl_Position.z/w (index.js:163) for the depth test against foreign geometry
             rec_out[2 * (size_t)i] = make_float4(cx, cy, a1x, a1y);
-            rec_out[2 * (size_t)i + 1] = make_float4(a2x, a2y, __uint_as_float(q.w), alpha);
+            rec_out[2 * (size_t)i + 1] = make_float4(a2x, a2y, __uint_as_float(q.w), zndc);
           }
         }
       }
@@ -415,9 +416,9 @@ __global__ void __launch_bounds__(kEmitThreads, 4) k_emit(const uint2 *__restric
           }
           bool keep = true;
           if (n_all > 1) {
-            // pixel-centre box of the tile, relative to the splat centre
-            const float xa = (float)(tx * kTile) + 0.5f - r0.x, xb = xa + 15.0f;
-            const float ya = (float)(ty * kTile) + 0.5f - r0.y, yb = ya + 15.0f;
+            // pixel-centre box of the bin, relative to the splat centre
+            const float xa = (float)(tx * kBin) + 0.5f - r0.x, xb = xa + (float)(kBin - 1);
+            const float ya = (float)(ty * kBin) + 0.5f - r0.y, yb = ya + (float)(kBin - 1);
             const bool in_x = (xa <= 0.0f) && (xb >= 0.0f), in_y = (ya <= 0.0f) && (yb >= 0.0f);
             if (!(in_x && in_y)) {
               float qmin = 3.0e38f;
@@ -438,7 +439,7 @@ __global__ void __launch_bounds__(kEmitThreads, 4) k_emit(const uint2 *__restric
           }
           uint32_t t = kNoTile;
           if (keep) {
-            t = ty * rc.tiles_x + tx;
+            t = ty * rc.bins_x + tx;
             atomicAdd(&s_hist[t & 255u], 1u);
           }
           const uint32_t q = p - wb;  // window-relative position

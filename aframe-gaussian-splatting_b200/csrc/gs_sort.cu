@@ -475,7 +475,7 @@ void launch_tile_radix(gs_context *c, FrameCounters *ctr, const FrameBufs &b, cu
 
 void launch_tile_ranges(gs_context *c, FrameCounters *ctr, const FrameBufs &b, cudaStream_t st) {
   const int grid = persistent_grid(c, c->cap_inst, 256 * 8, 8);
-  k_tile_ranges<<<grid, 256, 0, st>>>(c->inst_tile_f, ctr, b.tile_range);
+  k_tile_ranges<<<grid, 256, 0, st>>>(c->inst_tile_f, ctr, b.bin_range);
 }
 
 }  // namespace gs

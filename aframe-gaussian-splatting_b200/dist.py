@@ -1,7 +1,8 @@
 """Multi-GPU frame sharding: one process per GPU, torch.distributed for the plumbing.
 
 The reference has no multi-GPU path (one worker + one GL context).  Here the FRAME is sharded, not the splat
-table: rank r rasters the 16x16 tile columns with tx % world == r.  Every rank keeps the full 36 B/splat table
+table: rank r rasters the 64-pixel BIN columns bx with bx % world == r (a bin = 4x4 tiles of 16x16 pixels, the
+granularity splats are binned at).  Every rank keeps the full 36 B/splat table
 in its own HBM (80 M splats = 2.9 GB of 180 GB) and computes the same global draw order, so every pixel is
 composited on exactly one GPU in exactly the reference's order - the sharded frame is bit-identical to the
 single-GPU frame.  The only exchange step is one all-gather of finished RGBA tiles per frame
@@ -18,6 +19,7 @@ from typing import Callable, Optional
 import numpy as np
 
 TILE = 16
+BIN_TILES = 4  # tile columns per 64-pixel bin column
 
 
 @dataclass(frozen=True)
@@ -35,15 +37,21 @@ class TileSharding:
         return (self.height + TILE - 1) // TILE
 
     def owner(self, tx: int, ty: int) -> int:
-        """rank r owns the tile COLUMNS tx with tx % world == r (csrc/gs_common.cuh owned_cols / owned_slot)"""
-        return tx % self.world
+        """rank r owns the 64-pixel bin columns bx = tx // 4 with bx % world == r (csrc/gs_common.cuh owned_*)"""
+        return (tx // BIN_TILES) % self.world
 
     def owned_cols(self, rank: int) -> int:
-        return (self.tiles_x - 1 - rank) // self.world + 1 if rank < self.tiles_x else 0
+        """owned TILE columns: 4 per owned bin column, fewer in a partial last bin column (owned_tile_cols)"""
+        full, rem = divmod(self.tiles_x, BIN_TILES)
+        n = BIN_TILES * ((full - 1 - rank) // self.world + 1 if rank < full else 0)
+        if rem and full % self.world == rank:
+            n += rem
+        return n
 
     def slot(self, tx: int, ty: int, rank: int) -> int:
         """index of tile (tx, ty) inside rank's packed tile buffer (mirrors owned_slot)."""
-        return ty * self.owned_cols(rank) + (tx - rank) // self.world
+        bx = tx // BIN_TILES
+        return ty * self.owned_cols(rank) + (bx - rank) // self.world * BIN_TILES + tx % BIN_TILES
 
     def owned_tiles(self, rank: int) -> int:
         return self.tiles_y * self.owned_cols(rank)

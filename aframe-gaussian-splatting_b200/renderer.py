@@ -9,7 +9,7 @@ import numpy as np
 
 from . import _lib
 from ._lib import (GS_FORMAT_RGBA8, GS_FORMAT_RGBA32F, GS_RENDER_OUT_DEVICE, GS_RENDER_OUT_TILED,
-                   GS_RENDER_REUSE_SORT, GsRenderParams, GsStats)
+                   GS_RENDER_REUSE_SORT, GS_RENDER_STATS, GsRenderParams, GsStats)
 from .scenes import FrameInputs
 
 
@@ -102,7 +102,10 @@ class SplatContext:
         return out[:cnt.value] if readback else np.empty((0,), np.uint32)
 
     # -- draw --
-    def make_params(self, frame: FrameInputs, bg=(0.0, 0.0, 0.0, 0.0), fmt: int = GS_FORMAT_RGBA8, flags: int = 0) -> GsRenderParams:
+    def make_params(self, frame: FrameInputs, bg=(0.0, 0.0, 0.0, 0.0), fmt: int = GS_FORMAT_RGBA8, flags: int = 0,
+                    depth_in: Optional[np.ndarray] = None) -> GsRenderParams:
+        """depth_in: optional (H, W) float32 window-space depth of the geometry already drawn (index.js:179-180);
+        the returned struct keeps a reference to it."""
         p = GsRenderParams()
         p.proj[:] = [float(x) for x in np.asarray(frame.proj, np.float32).reshape(16)]
         p.modelview[:] = [float(x) for x in np.asarray(frame.modelview, np.float32).reshape(16)]
@@ -113,16 +116,23 @@ class SplatContext:
             p.cutout16[:] = [float(x) for x in np.asarray(frame.cutout, np.float32).reshape(16)]
         p.out_format = fmt
         p.flags = flags
+        if depth_in is not None:
+            d = np.ascontiguousarray(depth_in, dtype=np.float32)
+            if d.size != frame.width * frame.height:
+                raise ValueError("depth_in must hold width*height floats")
+            p._depth_keepalive = d
+            p.depth_in = d.ctypes.data
         return p
 
     def render(self, frame: FrameInputs, bg=(0.0, 0.0, 0.0, 0.0), fmt: int = GS_FORMAT_RGBA8, out: Optional[np.ndarray] = None,
-               reuse_sort: bool = False) -> np.ndarray:
+               reuse_sort: bool = False, depth_in: Optional[np.ndarray] = None, stats: bool = False) -> np.ndarray:
         """One frame into host memory: (H, W, 4) uint8 or float32, row 0 = bottom (GL orientation)."""
         dtype = np.uint8 if fmt == GS_FORMAT_RGBA8 else np.float32
         if out is None:
             out = np.empty((frame.height, frame.width, 4), dtype)
         assert out.dtype == dtype and out.size == frame.height * frame.width * 4 and out.flags["C_CONTIGUOUS"]
-        p = self.make_params(frame, bg, fmt, GS_RENDER_REUSE_SORT if reuse_sort else 0)
+        p = self.make_params(frame, bg, fmt, (GS_RENDER_REUSE_SORT if reuse_sort else 0) | (GS_RENDER_STATS if stats else 0),
+                             depth_in=depth_in)
         st = GsStats()
         self._check(self._lib.gs_render(self._h, C.byref(p), _ptr(out), C.byref(st)))
         self.last_stats = st

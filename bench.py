@@ -58,8 +58,10 @@ def load_peaks():
 
 def algorithmic_bytes(st: dict) -> dict:
     """SURVEY.md 8(d) per-frame algorithmic bytes, from the counters the library returns."""
-    # D = 16x16 tile instances whose tile really meets the r<=2 footprint (SURVEY.md 8: "D = sum of 16x16 tiles touched")
-    N, V, V2, D, T = st["n_splats"], st["n_sorted"], st["n_visible"], st["n_instances_kept"], st["n_tiles"]
+    # D = 16x16 tile instances whose tile really meets the r<=2 footprint (SURVEY.md 8: "D = sum of 16x16 tiles touched"),
+    # counted exactly by a GS_RENDER_STATS frame.  The library itself bins to 64x64-pixel bins (~4x fewer instances) and
+    # culls per tile inside the raster, so it MOVES fewer bytes than this formula charges.
+    N, V, V2, D, T = st["n_splats"], st["n_sorted"], st["n_visible"], st["n_tile_instances"], st["n_tiles"]
     P = st["width"] * st["height"]
     return {
         "sort": 20 * N + 8 * V,               # K1: 16 B centre + 4 B sizeAlpha read, depth + index write
@@ -411,6 +413,10 @@ def run_ours(args):
                 flush.zero_()
             lat_stats.append(ctx.wait(submit_device(i)).as_dict())
 
+        # ---- one diagnostic frame (untimed): exact D and the raster's pixel-splat pair counters ----
+        p_stats = ctx.make_params(fr, fmt=gs.GS_FORMAT_RGBA8, flags=flags | gs.GS_RENDER_STATS)
+        full_stats = ctx.wait(ctx.render_async(p_stats, (tiles_bufs[0] if sharded else frames_dev[0]).data_ptr())).as_dict()
+
         # ---- e2e: host buffers through the public C-ABI call, copies inside the timed region ----
         host_frames = [ctx.pinned_array((h, w, 4), np.uint8) for _ in range(3)]
         if not sharded:
@@ -467,6 +473,8 @@ def run_ours(args):
             st = {k: float(np.mean([s[k] for s in lat_stats])) for k in lat_stats[0]}
             for k in ("n_splats", "n_sorted", "n_visible", "n_instances", "n_instances_kept", "n_tiles", "width", "height", "kernel_launches", "n_dropped"):
                 st[k] = int(lat_stats[0][k])
+            for k2 in ("n_tile_instances", "n_records_streamed", "n_pair_tests", "n_pair_hits"):
+                st[k2] = int(full_stats[k2])
             ab = algorithmic_bytes(st)
             stage_ms = {"sort": st["ms_sort"], "project": st["ms_project"], "bin": st["ms_bin"], "raster": st["ms_raster"]}
             dom = max(stage_ms, key=stage_ms.get)
@@ -490,7 +498,12 @@ def run_ours(args):
             res = {
                 "metric": METRICS.get(name, METRIC), "value": fps, "unit": "frames/s", "ms_per_step": ms_per_step,
                 "config": config_block(args, name, n, w, h, orbit),
-                "counters": {k: st[k] for k in ("n_splats", "n_sorted", "n_visible", "n_instances", "n_instances_kept", "n_tiles", "n_dropped")},
+                "counters": {k: st[k] for k in ("n_splats", "n_sorted", "n_visible", "n_instances", "n_instances_kept", "n_tile_instances", "n_tiles", "n_dropped")},
+                "raster_pairs": {"tested": st["n_pair_tests"], "useful": st["n_pair_hits"],
+                                 "useful_frac": st["n_pair_hits"] / max(1, st["n_pair_tests"]),
+                                 "bin_records_streamed": st["n_records_streamed"], "tile_instances": st["n_tile_instances"],
+                                 "note": "pixel-splat pairs evaluated by live pixels vs pairs blended (r^2 <= 4), from one GS_RENDER_STATS frame "
+                                         "that walks every bin list to its end (a timed frame stops a tile once its pixels are saturated)"},
                 "msplats_per_s": n * fps / 1e6,
                 "e2e": e2e,
                 "gpu_launches": (int(st["kernel_launches"]) + (2 if use_peer else (1 if sharded else 0))) * steps,

@@ -58,9 +58,13 @@ enum {
                                      index.js:206,439-440: the draw uses a stale order)       */
   GS_RENDER_OUT_TILED = 1u << 2,  /* multi-GPU: write only the tiles this rank owns, packed as
                                      16x16 RGBA blocks in owned-tile order (see gs_set_shard) */
-  GS_RENDER_OUT_PEER = 1u << 3    /* multi-GPU, fused raster + exchange: every finished tile is stored
+  GS_RENDER_OUT_PEER = 1u << 3,   /* multi-GPU, fused raster + exchange: every finished tile is stored
                                      straight into ALL ranks' frames over NVLink peer memory (see
                                      gs_peer_export / gs_peer_import); no collective, no un-tiling */
+  GS_RENDER_STATS = 1u << 4,      /* also fill the gs_stats fields marked (STATS): exact count of 16x16 tile
+                                     instances and pixel-splat pair counters (a diagnostic frame: the raster
+                                     keeps culling closed tiles' lists, so it is slower than a plain frame)  */
+  GS_RENDER_DEPTH_DEVICE = 1u << 5 /* gs_render_params.depth_in is a device pointer (default: host memory)  */
 };
 
 /* Per-frame counters (SURVEY.md 8d symbols) and device timings of the last gs_sort/gs_render */
@@ -81,7 +85,13 @@ typedef struct gs_stats {
   float ms_total;          /* first kernel to last kernel of this frame on the device; with several
                               frames in flight it includes waiting behind the previous raster  */
   uint32_t kernel_launches;/* kernels launched by the call                                   */
-  uint32_t n_instances_kept;/* D  tile instances whose tile really meets the r<=2 footprint    */
+  uint32_t n_instances_kept;/*    BIN instances kept: 64x64-pixel bins really meeting the r<=2 footprint.
+                                  (n_instances counts the bounding-rectangle candidates.)  Splats are binned
+                                  to 64x64 bins; each 16x16 tile culls its bin's list in the raster.        */
+  uint64_t n_tile_instances;/* D  (STATS) 16x16 tiles meeting the footprint, summed over the drawn splats     */
+  uint64_t n_records_streamed;/*  (STATS) bin records the raster CTAs pulled through shared memory            */
+  uint64_t n_pair_tests;    /*    (STATS) pixel-splat pairs evaluated by live pixels                          */
+  uint64_t n_pair_hits;     /*    (STATS) pairs that passed r^2 <= 4 (and the depth test) and were blended   */
 } gs_stats;
 
 /* ---- lifetime ---------------------------------------------------------------------------- */
@@ -142,6 +152,11 @@ typedef struct gs_render_params {
   float cutout16[16];
   int32_t out_format;  /* GS_FORMAT_RGBA8 | GS_FORMAT_RGBA32F                                */
   uint32_t flags;      /* GS_RENDER_*                                                        */
+  const float *depth_in; /* optional depth buffer of the geometry already drawn (index.js:179-180:
+                          depthTest true, depthWrite false, three.js default LessEqualDepth): width*height
+                          f32 WINDOW-space depths in [0,1], row 0 = bottom.  A fragment is kept iff
+                          z/w*0.5+0.5 <= depth_in[pixel]; nothing is written back.  NULL = no depth test.
+                          Host memory unless GS_RENDER_DEPTH_DEVICE; must stay valid until gs_wait.     */
 } gs_render_params;
 
 /*

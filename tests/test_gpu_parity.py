@@ -271,7 +271,7 @@ def test_render_async_pipeline(gs, orc, ctx):
 
 def test_render_instance_overflow_regrows(gs, orc, ctx):
     """Huge splats touch every tile: the instance buffer overflows, is regrown and the frame re-run."""
-    n = 3000
+    n = 8000
     rows = gs.synth_splats(n, 77, log_scale_mean=-0.5)
     cs, cc, m = orc.pack(rows)
     with gs.SplatContext(0) as c2:
@@ -283,6 +283,40 @@ def test_render_instance_overflow_regrows(gs, orc, ctx):
         assert st["n_instances"] > (1 << 20)
         exp, _ = orc.render(cs, cc, orc.sort(m, fr.view), fr.proj, fr.modelview, 1920, 1080, fr.focal)
         assert np.abs(got - exp).max() <= FRAME_TOL
+
+
+def test_async_overflow_three_in_flight(gs, orc):
+    """three frames in flight all see the too-small instance buffer.  The first gs_wait must regrow ONCE to
+    the measured demand, the frames must be re-run in submission order, and every frame must equal its synchronous
+    render; a following REUSE_SORT frame must use the LAST submitted frame's order."""
+    n = 8000
+    rows = gs.synth_splats(n, 78, log_scale_mean=-0.5)
+    cs, cc, m = orc.pack(rows)
+    sc = gs.scenes
+    W, H = 1920, 1080
+    frames = [sc.make_frame(sc.orbit_camera(W, H, s), sc.demo_object(), W, H) for s in (0, 3, 6)]
+    with gs.SplatContext(0) as ref:
+        ref.push_packed(cs, cc, m[:, 15])
+        exp = [ref.render(f, fmt=gs.GS_FORMAT_RGBA8).copy() for f in frames]
+        demand = ref.stats()["n_instances"]
+        exp_reuse = ref.render(frames[0], fmt=gs.GS_FORMAT_RGBA8, reuse_sort=True).copy()  # camera 0 drawn with frame 2's order
+    assert demand > (1 << 20)
+    with gs.SplatContext(0) as c2:
+        c2.push_packed(cs, cc, m[:, 15])
+        outs = [c2.pinned_array((H, W, 4), np.uint8) for _ in frames]
+        tickets = [c2.render_async(c2.make_params(f, fmt=gs.GS_FORMAT_RGBA8), o.ctypes.data) for f, o in zip(frames, outs)]
+        for t in tickets:
+            st = c2.wait(t)
+        assert st.n_instances == demand or st.n_instances > (1 << 20)
+        for o, e in zip(outs, exp):
+            assert np.array_equal(o, e)
+        got_reuse = c2.render(frames[0], fmt=gs.GS_FORMAT_RGBA8, reuse_sort=True)
+        assert np.array_equal(got_reuse, exp_reuse)
+        # waiting out of order works too (the older frames are finished first)
+        tickets = [c2.render_async(c2.make_params(f, fmt=gs.GS_FORMAT_RGBA8), o.ctypes.data) for f, o in zip(frames, outs)]
+        c2.wait(tickets[2]); c2.wait(tickets[0]); c2.wait(tickets[1])
+        for o, e in zip(outs, exp):
+            assert np.array_equal(o, e)
 
 
 def test_full_size_properties(gs, ctx):

@@ -33,8 +33,9 @@ def test_no_cpu_fallback_without_gpu(gs):
 
 
 def test_struct_layouts_match_header(gs):
-    assert ctypes.sizeof(gs.GsRenderParams) == 16 * 4 * 2 + 4 + 4 + 4 + 16 + 4 + 64 + 4 + 4
-    assert ctypes.sizeof(gs.GsStats) == 88
+    assert ctypes.sizeof(gs.GsRenderParams) == 16 * 4 * 2 + 4 + 4 + 4 + 16 + 4 + 64 + 4 + 4 + 8  # + depth_in pointer
+    assert gs.GsRenderParams.depth_in.offset == 232
+    assert ctypes.sizeof(gs.GsStats) == 88 + 4 * 8  # + n_tile_instances, n_records_streamed, n_pair_tests, n_pair_hits
 
 
 def test_owned_tiles_partition(gs):
@@ -43,10 +44,10 @@ def test_owned_tiles_partition(gs):
         tiles = ((w + 15) // 16) * ((h + 15) // 16)
         for world in (1, 2, 3, 4, 8):
             counts = [lib.gs_owned_tiles(w, h, r, world) for r in range(world)]
-            assert sum(counts) == tiles and max(counts) - min(counts) <= (h + 15) // 16
+            assert sum(counts) == tiles and max(counts) - min(counts) <= 4 * ((h + 15) // 16)
             tx, ty = np.meshgrid(np.arange((w + 15) // 16), np.arange((h + 15) // 16))
-            for r in range(world):
-                assert counts[r] == int(((tx % world) == r).sum())
+            for r in range(world):  # rank r owns the 64-pixel bin columns bx = tx // 4 with bx % world == r
+                assert counts[r] == int((((tx // 4) % world) == r).sum())
 
 
 def test_synth_is_deterministic_and_ordered(gs):
