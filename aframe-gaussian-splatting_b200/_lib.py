@@ -47,6 +47,7 @@ SYMBOLS = {
     "gs_version": (C.c_char_p, []),
     "gs_clear": (C.c_int, [_P]),
     "gs_push_splats": (C.c_int, [_P, _P, C.c_uint32]),
+    "gs_reserve": (C.c_int, [_P, C.c_uint32]),
     "gs_push_packed": (C.c_int, [_P, _P, _P, _P, C.c_uint32]),
     "gs_num_splats": (C.c_int, [_P, C.POINTER(C.c_uint32)]),
     "gs_read_packed": (C.c_int, [_P, C.c_uint32, C.c_uint32, _P, _P, _P]),
@@ -54,6 +55,8 @@ SYMBOLS = {
     "gs_render": (C.c_int, [_P, C.POINTER(GsRenderParams), _P, C.POINTER(GsStats)]),
     "gs_render_async": (C.c_int, [_P, C.POINTER(GsRenderParams), _P, C.POINTER(C.c_uint64)]),
     "gs_wait": (C.c_int, [_P, C.c_uint64, C.POINTER(GsStats)]),
+    "gs_render_stereo": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(GsRenderParams), C.POINTER(_P),
+                                   C.POINTER(GsStats)]),
     "gs_read_projected": (C.c_int, [_P, C.c_uint32, C.c_uint32, _P]),
     "gs_get_stats": (C.c_int, [_P, C.POINTER(GsStats)]),
     "gs_set_shard": (C.c_int, [_P, C.c_uint32, C.c_uint32]),

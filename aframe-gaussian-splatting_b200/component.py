@@ -100,8 +100,11 @@ class GaussianSplattingComponent:
 
     # ---- index.js:25-221 ----
     def initGL(self, numVertexes: int) -> None:
-        """The reference allocates two data textures of MAX_TEXTURE_SIZE^2 texels; the device table grows on
-        push, so there is nothing to pre-size.  sortReady flips exactly as at index.js:220."""
+        """The reference sizes its two data textures from numVertexes (index.js:26-46, known from the Content-Length,
+        index.js:248-251); here the resident table is reserved for as many splats, so the pushes that follow never
+        have to grow it (and never wait for frames in flight).  sortReady flips exactly as at index.js:220."""
+        if numVertexes > 0 and self.renderer is not None:
+            self.renderer.reserve(int(numVertexes))
         self.sortReady = True
 
     # ---- index.js:222-327 ----
@@ -117,9 +120,11 @@ class GaussianSplattingComponent:
             is_ply = str(src).endswith(".ply")  # index.js:257
             with open(os.fspath(src), "rb") as f:
                 buf = np.frombuffer(f.read(), dtype=np.uint8)
-        self.initGL(len(buf) // self.rowLength)  # index.js:249-250
         if is_ply:
+            # a .ply is converted first and sized afterwards, the reference's path when no Content-Length is known
+            # (index.js:315-323); sizing from the raw byte count (index.js:249-250) would over-reserve 248/32 x (Q11)
             buf = np.frombuffer(self.processPlyBuffer(buf.tobytes()), dtype=np.uint8)  # index.js:315-317
+        self.initGL(len(buf) // self.rowLength)  # index.js:249-250 / 320-323
         # progressive push in chunks, whole rows only (index.js:279-298); a trailing partial row is dropped
         n_rows = len(buf) // self.rowLength
         chunk = 1 << 22
@@ -162,18 +167,40 @@ class GaussianSplattingComponent:
         return get_model_view_matrix(camera or self.camera, self.object)
 
     # ---- index.js:184-195 + the instanced draw ----
-    def frame_inputs(self, width: int, height: int, camera=None) -> FrameInputs:
+    def _frame_inputs_px(self, w: int, h: int, camera=None) -> FrameInputs:
+        """onBeforeRender (index.js:184-195) for a viewport of w x h device pixels."""
         proj = self.getProjectionMatrix(camera)
         mv = self.getModelViewMatrix(camera)
-        # renderer.setPixelRatio: three.js floors the drawing-buffer size and the current viewport
-        # (Math.floor(width * pixelRatio), viewport.multiplyScalar(pixelRatio).floor())
-        w, h = int(math.floor(width * self.pixelRatio)), int(math.floor(height * self.pixelRatio))
         cut = None
         if self.cutout is not None:
             cut = np.asarray(world_to_cutout(self.cutout, self.object).elements, dtype=np.float32)
         return FrameInputs(proj=np.asarray(proj.elements, np.float32), modelview=np.asarray(mv.elements, np.float32),
                            view=np.array([mv.elements[2], mv.elements[6], mv.elements[10], mv.elements[14]], np.float32),
                            width=w, height=h, focal=float(np.float32(focal_length(h, proj))), cutout=cut)
+
+    def frame_inputs(self, width: int, height: int, camera=None) -> FrameInputs:
+        # renderer.setPixelRatio: three.js floors the drawing-buffer size and the current viewport
+        # (Math.floor(width * pixelRatio), viewport.multiplyScalar(pixelRatio).floor())
+        w, h = int(math.floor(width * self.pixelRatio)), int(math.floor(height * self.pixelRatio))
+        return self._frame_inputs_px(w, h, camera)
+
+    def render_xr(self, eye_cameras, width: int, height: int, bg=(0.0, 0.0, 0.0, 0.0), fmt: int = GS_FORMAT_RGBA8):
+        """WebXR presentation (index.js:13-15, 184-195).  `init` hands `xrPixelRatio` to
+        renderer.xr.setFramebufferScaleFactor, so each eye's viewport is the XR layer's native eye size
+        (width x height) scaled by it (floored here).  The frame's single sort request comes from tick(), i.e. from
+        `this.camera` - the head pose - (index.js:438-455), while material.onBeforeRender runs once per eye camera
+        with that eye's matrices and viewport.  Returns [left, right] frames, row 0 = bottom."""
+        ratio = float(self.data.get("xrPixelRatio") or 0)
+        if ratio <= 0:
+            ratio = 1.0
+        w, h = int(math.floor(width * ratio)), int(math.floor(height * ratio))
+        eyes = [self._frame_inputs_px(w, h, cam) for cam in eye_cameras]
+        head = self.getModelViewMatrix().elements
+        view = np.array([head[2], head[6], head[10], head[14]], dtype=np.float32)  # index.js:441-442
+        cut = eyes[0].cutout
+        frames = self.renderer.render_stereo(view, eyes, cutout=cut, bg=bg, fmt=fmt)
+        self._have_order = True
+        return frames
 
     def render(self, width: int, height: int, camera=None, bg=(0.0, 0.0, 0.0, 0.0), fmt: int = GS_FORMAT_RGBA8,
                out: Optional[np.ndarray] = None, synchronous: bool = True) -> np.ndarray:

@@ -50,10 +50,14 @@ static void dev_free(T *&p) {
 // ---------------------------------------------------------------------------------------------
 // capacity management
 // ---------------------------------------------------------------------------------------------
-static int ensure_table(gs_context *c, uint64_t need) {
+// Grow the resident table to hold `need` splats.  Growth is geometric (or exact, through gs_reserve) and is the one
+// moment a push has to wait for the frames in flight: they read the buffers that are about to be replaced.
+static int ensure_table(gs_context *c, uint64_t need, bool exact = false) {
   if (need <= c->cap) return GS_OK;
   if (need > 0x7FFFFFFFull) return fail(c, GS_ERR_CAPACITY, "more than 2^31-1 splats");
-  uint64_t ncap = std::max<uint64_t>(need, (uint64_t)c->cap * 2);
+  int rc0 = drain(c);
+  if (rc0) return rc0;
+  uint64_t ncap = exact ? need : std::max<uint64_t>(need, (uint64_t)c->cap * 2);
   ncap = std::min<uint64_t>(std::max<uint64_t>(ncap, 1024), 0x7FFFFFFFull);
   float4 *cs = nullptr;
   uint4 *cc = nullptr;
@@ -62,11 +66,11 @@ static int ensure_table(gs_context *c, uint64_t need) {
   GS_CUDA(c, dev_alloc(&cc, ncap));
   GS_CUDA(c, dev_alloc(&sa, ncap));
   if (c->n) {
-    GS_CUDA(c, cudaMemcpyAsync(cs, c->center_scale, sizeof(float4) * c->n, cudaMemcpyDeviceToDevice, c->stream));
-    GS_CUDA(c, cudaMemcpyAsync(cc, c->cov_color, sizeof(uint4) * c->n, cudaMemcpyDeviceToDevice, c->stream));
-    GS_CUDA(c, cudaMemcpyAsync(sa, c->size_alpha, sizeof(float) * c->n, cudaMemcpyDeviceToDevice, c->stream));
-    GS_CUDA(c, cudaStreamSynchronize(c->stream));
+    GS_CUDA(c, cudaMemcpyAsync(cs, c->center_scale, sizeof(float4) * c->n, cudaMemcpyDeviceToDevice, c->push_stream));
+    GS_CUDA(c, cudaMemcpyAsync(cc, c->cov_color, sizeof(uint4) * c->n, cudaMemcpyDeviceToDevice, c->push_stream));
+    GS_CUDA(c, cudaMemcpyAsync(sa, c->size_alpha, sizeof(float) * c->n, cudaMemcpyDeviceToDevice, c->push_stream));
   }
+  GS_CUDA(c, cudaStreamSynchronize(c->push_stream));
   dev_free(c->center_scale);
   dev_free(c->cov_color);
   dev_free(c->size_alpha);
@@ -205,6 +209,10 @@ extern "C" int gs_create(int device_ordinal, gs_context **out_ctx) {
   if ((e = cudaStreamCreateWithPriority(&c->bstream, cudaStreamNonBlocking, prio_greatest)) != cudaSuccess) return bail("cudaStreamCreate", e);
   if ((e = cudaStreamCreateWithPriority(&c->rstream, cudaStreamNonBlocking, prio_least)) != cudaSuccess) return bail("cudaStreamCreate", e);
   if ((e = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+  if ((e = cudaStreamCreateWithFlags(&c->push_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+  for (int i = 0; i < 2; ++i)
+    if ((e = cudaEventCreateWithFlags(&c->push_ev[i], cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
+  if ((e = cudaEventCreateWithFlags(&c->push_done, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
   for (int i = 0; i < 3; ++i) c->slot[i].index = i;
   if ((e = cudaStreamCreateWithPriority(&c->aux_stream, cudaStreamNonBlocking, prio_greatest)) != cudaSuccess) return bail("cudaStreamCreate", e);
   for (int i = 0; i < 2; ++i) {
@@ -265,6 +273,14 @@ extern "C" int gs_destroy(gs_context *c) {
   dev_free(c->bin_range[0]); dev_free(c->bin_range[1]); dev_free(c->quirk_table); dev_free(c->tile_stats);
   if (c->tile_stats_host) cudaFreeHost(c->tile_stats_host);
   if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
+  if (c->push_stream) cudaStreamSynchronize(c->push_stream);
+  for (int i = 0; i < 2; ++i) {
+    if (c->push_pinned[i]) cudaFreeHost(c->push_pinned[i]);
+    dev_free(c->push_dev[i]);
+    if (c->push_ev[i]) cudaEventDestroy(c->push_ev[i]);
+  }
+  if (c->push_done) cudaEventDestroy(c->push_done);
+  if (c->push_stream) cudaStreamDestroy(c->push_stream);
   drop_graphs(c);
   for (uint32_t r = 0; r < c->peer_world; ++r)
     if (r != c->peer_rank && c->peer_base[r]) cudaIpcCloseMemHandle(c->peer_base[r]);
@@ -307,6 +323,7 @@ extern "C" int gs_clear(gs_context *c) {
   if (!c) return GS_ERR_INVALID;
   int rc0 = drain(c);
   if (rc0) return rc0;
+  GS_CUDA(c, cudaStreamSynchronize(c->push_stream));
   c->n = 0;
   c->have_order = false;
   c->order_count = 0;
@@ -319,24 +336,48 @@ extern "C" int gs_num_splats(const gs_context *c, uint32_t *out_n) {
   return GS_OK;
 }
 
+// pinned + device staging for the push path, created on first use
+static int ensure_push_staging(gs_context *c) {
+  if (c->push_dev[1]) return GS_OK;
+  const size_t bytes = (size_t)gs_context::kPushRows * 32;
+  for (int i = 0; i < 2; ++i) {
+    if (!c->push_pinned[i]) GS_CUDA(c, cudaHostAlloc(&c->push_pinned[i], bytes, cudaHostAllocDefault));
+    if (!c->push_dev[i]) GS_CUDA(c, cudaMalloc((void **)&c->push_dev[i], bytes));
+  }
+  return GS_OK;
+}
+
+extern "C" int gs_reserve(gs_context *c, uint32_t n_total) {
+  if (!c) return GS_ERR_INVALID;
+  GS_CUDA(c, cudaSetDevice(c->device));
+  return ensure_table(c, n_total, /*exact=*/true);
+}
+
 extern "C" int gs_push_splats(gs_context *c, const void *rows32, uint32_t n) {
   if (!c || (!rows32 && n)) return GS_ERR_INVALID;
   if (!n) return GS_OK;
   GS_CUDA(c, cudaSetDevice(c->device));
-  int rc = drain(c);
-  if (rc) return rc;
+  int rc;
   if ((rc = ensure_table(c, (uint64_t)c->n + n))) return rc;
-  uint8_t *rows_dev = nullptr;
-  GS_CUDA(c, cudaMalloc((void **)&rows_dev, (size_t)n * 32));
-  cudaError_t e = cudaMemcpyAsync(rows_dev, rows32, (size_t)n * 32, cudaMemcpyHostToDevice, c->stream);
-  if (e == cudaSuccess) {
-    launch_pack(c, rows_dev, c->n, n);
-    e = cudaGetLastError();
+  if ((rc = ensure_push_staging(c))) return rc;
+  // Frames in flight keep rendering: they read rows [0, n_at_submit) only, the pack below writes rows >= c->n, on
+  // its own stream.  Chunks alternate between two pinned staging buffers, so the host copy of chunk k+1 overlaps the
+  // DMA + pack of chunk k.  The caller's buffer is fully consumed when this returns.
+  const uint8_t *src = (const uint8_t *)rows32;
+  for (uint32_t off = 0; off < n; off += gs_context::kPushRows) {
+    const uint32_t m = std::min<uint32_t>(gs_context::kPushRows, n - off);
+    const int b = c->push_buf;
+    c->push_buf ^= 1;
+    GS_CUDA(c, cudaEventSynchronize(c->push_ev[b]));  // this staging pair's previous chunk has been packed
+    memcpy(c->push_pinned[b], src + (size_t)off * 32, (size_t)m * 32);
+    GS_CUDA(c, cudaMemcpyAsync(c->push_dev[b], c->push_pinned[b], (size_t)m * 32, cudaMemcpyHostToDevice, c->push_stream));
+    launch_pack(c, c->push_dev[b], c->n + off, m, c->push_stream);
+    GS_CUDA(c, cudaGetLastError());
+    GS_CUDA(c, cudaEventRecord(c->push_ev[b], c->push_stream));
   }
-  if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
-  cudaFree(rows_dev);
-  GS_CUDA(c, e);
+  GS_CUDA(c, cudaEventRecord(c->push_done, c->push_stream));
   c->n += n;
+  c->pushed = true;
   c->have_order = false;
   return GS_OK;
 }
@@ -346,14 +387,15 @@ extern "C" int gs_push_packed(gs_context *c, const float *center_scale4, const u
   if (!c || ((!center_scale4 || !cov_color4 || !size_alpha) && n)) return GS_ERR_INVALID;
   if (!n) return GS_OK;
   GS_CUDA(c, cudaSetDevice(c->device));
-  int rc = drain(c);
-  if (rc) return rc;
+  int rc;
   if ((rc = ensure_table(c, (uint64_t)c->n + n))) return rc;
-  GS_CUDA(c, cudaMemcpyAsync(c->center_scale + c->n, center_scale4, sizeof(float4) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
-  GS_CUDA(c, cudaMemcpyAsync(c->cov_color + c->n, cov_color4, sizeof(uint4) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
-  GS_CUDA(c, cudaMemcpyAsync(c->size_alpha + c->n, size_alpha, sizeof(float) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
-  GS_CUDA(c, cudaStreamSynchronize(c->stream));
+  GS_CUDA(c, cudaMemcpyAsync(c->center_scale + c->n, center_scale4, sizeof(float4) * (size_t)n, cudaMemcpyHostToDevice, c->push_stream));
+  GS_CUDA(c, cudaMemcpyAsync(c->cov_color + c->n, cov_color4, sizeof(uint4) * (size_t)n, cudaMemcpyHostToDevice, c->push_stream));
+  GS_CUDA(c, cudaMemcpyAsync(c->size_alpha + c->n, size_alpha, sizeof(float) * (size_t)n, cudaMemcpyHostToDevice, c->push_stream));
+  GS_CUDA(c, cudaStreamSynchronize(c->push_stream));  // pageable sources: the caller may reuse them on return
+  GS_CUDA(c, cudaEventRecord(c->push_done, c->push_stream));
   c->n += n;
+  c->pushed = true;
   c->have_order = false;
   return GS_OK;
 }
@@ -362,6 +404,7 @@ extern "C" int gs_read_packed(gs_context *c, uint32_t first, uint32_t n, float *
                               float *size_alpha) {
   if (!c || (uint64_t)first + n > c->n) return GS_ERR_INVALID;
   GS_CUDA(c, cudaSetDevice(c->device));
+  GS_CUDA(c, cudaStreamSynchronize(c->push_stream));  // pushes are asynchronous
   if (center_scale4) GS_CUDA(c, cudaMemcpy(center_scale4, c->center_scale + first, sizeof(float4) * (size_t)n, cudaMemcpyDeviceToHost));
   if (cov_color4) GS_CUDA(c, cudaMemcpy(cov_color4, c->cov_color + first, sizeof(uint4) * (size_t)n, cudaMemcpyDeviceToHost));
   if (size_alpha) GS_CUDA(c, cudaMemcpy(size_alpha, c->size_alpha + first, sizeof(float) * (size_t)n, cudaMemcpyDeviceToHost));
@@ -388,9 +431,9 @@ static int drain(gs_context *c) {
   return GS_OK;
 }
 
-static void stats_from_counters(gs_context *c, const FrameCounters &h) {
+static void stats_from_counters(gs_context *c, const FrameCounters &h, uint32_t n_splats) {
   gs_stats &s = c->stats;
-  s.n_splats = c->n;
+  s.n_splats = n_splats;
   s.n_sorted = h.sort.n_valid;
   s.n_dropped = h.sort.n_dropped;
   s.n_visible = h.n_visible;
@@ -415,18 +458,20 @@ extern "C" int gs_sort(gs_context *c, const float view[4], const float *cutout16
   const FrameBufs bufs{c->order[0], c->proj_rec[0], c->rect[0], c->inst_rec[0], c->bin_range[0]};
   memset(sl.fp_host, 0, sizeof(FrameParams));
   fill_sort_consts(sl.fp_host->sc, view, cutout16_or_null);
+  sl.fp_host->n_splats = c->n;
+  if (c->pushed) GS_CUDA(c, cudaStreamWaitEvent(c->stream, c->push_done, 0));
   GS_CUDA(c, cudaMemcpyAsync(sl.fp, sl.fp_host, sizeof(FrameParams), cudaMemcpyHostToDevice, c->stream));
   GS_CUDA(c, cudaMemsetAsync(sl.ctr, 0, sizeof(FrameCounters), c->stream));
   GS_CUDA(c, cudaEventRecord(c->ev[0], c->stream));
   launch_depth_cull(c, sl.fp, sl.ctr, c->stream);
-  launch_depth_radix(c, sl.ctr, bufs, c->stream);
+  launch_depth_radix(c, sl.fp, sl.ctr, bufs, c->stream);
   GS_CUDA(c, cudaGetLastError());
   GS_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
   GS_CUDA(c, cudaMemcpyAsync(c->sort_hdr, sl.ctr, sizeof(SortHeader), cudaMemcpyDeviceToDevice, c->stream));
   GS_CUDA(c, cudaMemcpyAsync(sl.ctr_host, sl.ctr, sizeof(FrameCounters), cudaMemcpyDeviceToHost, c->stream));
   GS_CUDA(c, cudaStreamSynchronize(c->stream));
   memset(&c->stats, 0, sizeof(c->stats));
-  stats_from_counters(c, *sl.ctr_host);
+  stats_from_counters(c, *sl.ctr_host, sl.fp_host->n_splats);
   c->stats.kernel_launches = 7;
   float ms = 0;
   cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]);
@@ -484,7 +529,7 @@ static cudaError_t enqueue_sort_stage(gs_context *c, gs_context::Slot &sl, bool 
   if ((e = rec(sl.evp[1], x))) return e;
   if ((e = cudaEventRecord(c->ev_join[0], x))) return e;
   if (!reuse) {
-    launch_depth_radix(c, sl.ctr, b, m);
+    launch_depth_radix(c, sl.fp, sl.ctr, b, m);
     if ((e = cudaMemcpyAsync(c->sort_hdr, sl.ctr, sizeof(SortHeader), cudaMemcpyDeviceToDevice, m))) return e;
   }
   if ((e = rec(sl.ev[1], m))) return e;
@@ -556,7 +601,7 @@ static int run_graph(gs_context *c, cudaGraphExec_t &ge, cudaStream_t stream, F 
 static int launch_frame(gs_context *c, gs_context::Slot &sl, bool reuse, uint32_t n_tiles, uint32_t n_bins) {
   // (re)capture when anything baked into the launches changed
   gs_context::GraphKey k;
-  k.n = c->n; k.n_tiles = n_tiles; k.cap_inst = c->cap_inst; k.p0 = c->depth; k.p1 = c->inst_rec[0]; k.p2 = c->center_scale;
+  k.cap = c->cap; k.n_tiles = n_tiles; k.cap_inst = c->cap_inst; k.p0 = c->depth; k.p1 = c->inst_rec[0]; k.p2 = c->center_scale;
   if (memcmp(&k, &c->gkey, sizeof(k)) != 0) {
     drop_graphs(c);
     c->gkey = k;
@@ -607,6 +652,8 @@ static int submit(gs_context *c, gs_context::Slot &sl) {
   FrameParams &fp = *sl.fp_host;
   RenderConsts &rc = fp.rc;
   memset(&fp, 0, sizeof(fp));
+  fp.n_splats = sl.n_splats;  // what was resident when the frame was submitted; later pushes append behind it
+  if (c->pushed) GS_CUDA(c, cudaStreamWaitEvent(c->stream, c->push_done, 0));
   memcpy(rc.proj, p->proj, sizeof(rc.proj));
   memcpy(rc.mv, p->modelview, sizeof(rc.mv));
   rc.width = p->width;
@@ -741,7 +788,7 @@ static int wait_slot(gs_context *c, gs_context::Slot &sl, gs_stats *stats) {
     if ((rcode = submit(c, sl))) return rcode;
   }
   memset(&c->stats, 0, sizeof(c->stats));
-  stats_from_counters(c, *sl.ctr_host);
+  stats_from_counters(c, *sl.ctr_host, sl.fp_host->n_splats);
   c->stats.kernel_launches = sl.launches;
   c->stats.n_tiles = sl.fp_host->rc.n_tiles;
   if (sl.raster_flags & 4u) {  // GS_RENDER_STATS: per-tile {records streamed, records kept, pair tests, pair hits}
@@ -792,11 +839,18 @@ extern "C" int gs_render_async(gs_context *c, const gs_render_params *p, void *o
     if ((rcode = ensure_scratch(c))) return rcode;
     if ((rcode = ensure_bins(c, n_bins))) return rcode;
     if ((rcode = ensure_tile_stats(c, n_tiles))) return rcode;
-    if (c->cap_inst == 0 && (rcode = ensure_instances(c, std::max<uint64_t>(1u << 20, (uint64_t)c->n * 4)))) return rcode;
+    if (c->cap_inst == 0) {
+      // first frame: room for two bin instances per resident splat (a typical scene needs ~1); GS_INST_CAP overrides
+      // the initial size (tests of the overflow / regrow path)
+      uint64_t first = std::max<uint64_t>(1u << 20, (uint64_t)c->n * 2);
+      if (const char *e = getenv("GS_INST_CAP")) first = std::max<uint64_t>(1024, strtoull(e, nullptr, 10));
+      if ((rcode = ensure_instances(c, first))) return rcode;
+    }
   }
   sl.params = *p;
   sl.out_user = out_rgba;
   sl.ticket = ticket;
+  sl.n_splats = c->n;
   if ((rcode = submit(c, sl))) return rcode;
   c->next_ticket = ticket + 1;
   if (out_ticket) *out_ticket = ticket;
@@ -820,6 +874,27 @@ extern "C" int gs_render(gs_context *c, const gs_render_params *p, void *out_rgb
   int rc = gs_render_async(c, p, out_rgba, &t);
   if (rc) return rc;
   return gs_wait(c, t, stats);
+}
+
+// XR: one sort request per frame from the head camera (tick(), index.js:438-455), one draw per eye with that eye's
+// matrices and viewport (onBeforeRender per eye camera, index.js:184-195)
+extern "C" int gs_render_stereo(gs_context *c, const float view[4], const float *cutout16_or_null,
+                                const gs_render_params eyes[2], void *const out_rgba[2], gs_stats *stats2_or_null) {
+  if (!c || !view || !eyes || !out_rgba || !out_rgba[0] || !out_rgba[1]) return GS_ERR_INVALID;
+  int rc = gs_sort(c, view, cutout16_or_null, nullptr, nullptr);
+  if (rc) return rc;
+  const float ms_sort = c->stats.ms_sort;
+  for (int e = 0; e < 2; ++e) {
+    gs_render_params p = eyes[e];
+    p.flags |= GS_RENDER_REUSE_SORT;  // both eyes draw with the head camera's order
+    gs_stats st;
+    if ((rc = gs_render(c, &p, out_rgba[e], &st))) return rc;
+    if (stats2_or_null) {
+      stats2_or_null[e] = st;
+      stats2_or_null[e].ms_sort = e == 0 ? ms_sort : 0.0f;  // the one sort is accounted to the first eye
+    }
+  }
+  return GS_OK;
 }
 
 extern "C" int gs_peer_export(gs_context *c, size_t frame_bytes, void *handle_out) {

@@ -86,6 +86,7 @@ constexpr int kMaxPeers = 16;
 struct FrameParams {
   SortConsts sc;
   RenderConsts rc;
+  uint32_t n_splats;  // resident splats of THIS frame (the table may be growing behind it: progressive push)
   void *out;  // frame (or packed owned tiles) destination of the raster
   const void *depth_in;  // optional window-space depth of foreign geometry (f32, width*height, row 0 = bottom)
   // ---- fused raster + exchange over NVLink peer memory (GS_RENDER_OUT_PEER) ----
@@ -166,6 +167,7 @@ struct gs_context {
     void *depth_dev = nullptr;               // staging of a host depth_in
     size_t depth_bytes = 0;
     uint32_t raster_flags = 0;               // k_raster instantiation of this frame (packed | depth | stats)
+    uint32_t n_splats = 0;                   // resident splats when the frame was submitted
     cudaEvent_t ev[5]{};                     // stage boundaries (timing)
     cudaEvent_t evp[2]{};                    // k_project on the aux stream (timing)
     cudaEvent_t ev_done = nullptr, ev_copied = nullptr;
@@ -198,12 +200,22 @@ struct gs_context {
   int last_set = 0;                                 // set holding the most recent sort (GS_RENDER_REUSE_SORT, read-backs)
   cudaStream_t rstream = nullptr;   // raster stream: frame k is rasterised here while frame k+1 is sorted / binned
   cudaStream_t copy_stream = nullptr;
+  // ---- progressive push (index.js:259-298, 576-586): rows go host -> pinned staging -> device staging -> k_pack on
+  // their own stream while frames keep rendering the prefix that was resident when they were submitted ----
+  cudaStream_t push_stream = nullptr;
+  static constexpr uint32_t kPushRows = 1u << 18;  // rows per staging buffer (8 MiB)
+  void *push_pinned[2] = {nullptr, nullptr};
+  uint8_t *push_dev[2] = {nullptr, nullptr};
+  cudaEvent_t push_ev[2] = {nullptr, nullptr};      // staging buffer i is free again
+  cudaEvent_t push_done = nullptr;                  // everything pushed so far is packed
+  int push_buf = 0;
+  bool pushed = false;
   cudaStream_t aux_stream = nullptr;             // runs k_project beside the depth radix passes
   cudaEvent_t ev_fork[2]{}, ev_join[2]{};
   bool use_graphs = true;
   uint32_t raster_base_flags = 1;                // default pixel loop: 1 = packed fp32x2, 0 = scalar
   // graph cache key: anything baked into the captured launches
-  struct GraphKey { uint32_t n = 0, n_tiles = 0; uint64_t cap_inst = 0; const void *p0 = nullptr, *p1 = nullptr, *p2 = nullptr; } gkey;
+  struct GraphKey { uint32_t cap = 0, n_tiles = 0; uint64_t cap_inst = 0; const void *p0 = nullptr, *p1 = nullptr, *p2 = nullptr; } gkey;
 
   // ---- fused exchange: one shared allocation per rank = flag rows + a ring of 3 frames, opened by every peer ----
   void *peer_local = nullptr;            // our shared block
@@ -238,8 +250,8 @@ struct FrameBufs {
 
 // -- launchers (each .cu file owns its kernels); every per-frame input comes from device memory (fp, ctr) --
 void launch_depth_cull(gs_context *c, const FrameParams *fp, FrameCounters *ctr, cudaStream_t st);
-void launch_depth_radix(gs_context *c, FrameCounters *ctr, const FrameBufs &b, cudaStream_t st);  // 6 launches -> b.order
-void launch_pack(gs_context *c, const uint8_t *rows_dev, uint32_t first, uint32_t n);
+void launch_depth_radix(gs_context *c, const FrameParams *fp, FrameCounters *ctr, const FrameBufs &b, cudaStream_t st);  // 6 launches -> b.order
+void launch_pack(gs_context *c, const uint8_t *rows_dev, uint32_t first, uint32_t n, cudaStream_t st);
 void launch_project(gs_context *c, const FrameParams *fp, const FrameBufs &b, cudaStream_t st);
 void launch_emit(gs_context *c, const FrameParams *fp, FrameCounters *ctr, const FrameBufs &b, cudaStream_t st);  // 2 launches
 void launch_tile_radix(gs_context *c, FrameCounters *ctr, const FrameBufs &b, cudaStream_t st);  // 5 launches

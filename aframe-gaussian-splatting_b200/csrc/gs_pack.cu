@@ -113,10 +113,10 @@ __global__ void __launch_bounds__(256) k_pack(const uint4 *__restrict__ rows, ui
   sa[o] = (float)__ddiv_rn(__dmul_rn(ms, (double)(rgba >> 24)), 255.0);
 }
 
-void launch_pack(gs_context *c, const uint8_t *rows_dev, uint32_t first, uint32_t n) {
+void launch_pack(gs_context *c, const uint8_t *rows_dev, uint32_t first, uint32_t n, cudaStream_t st) {
   if (!n) return;
   const uint32_t grid = (n + 255) / 256;
-  k_pack<<<grid, 256, 0, c->stream>>>((const uint4 *)rows_dev, first, n, c->center_scale, c->cov_color, c->size_alpha,
+  k_pack<<<grid, 256, 0, st>>>((const uint4 *)rows_dev, first, n, c->center_scale, c->cov_color, c->size_alpha,
                                       c->quirk_table, c->quirk_n);
 }
 

@@ -35,10 +35,11 @@ __device__ __forceinline__ void unpack_int16(uint32_t value, float &lo, float &h
 // the reference may draw through the zero tail of quirk Q5.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_project(const float4 *__restrict__ cs, const uint4 *__restrict__ cc,
-                                                 const float *__restrict__ depth, uint32_t n,
+                                                 const float *__restrict__ depth,
                                                  const FrameParams *__restrict__ fp, float4 *__restrict__ rec_out,
                                                  uint32_t *__restrict__ rect_out) {
   const RenderConsts &rc = fp->rc;
+  const uint32_t n = fp->n_splats;
   const uint32_t stride = gridDim.x * blockDim.x;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     uint32_t rect = kNoRect;
@@ -470,15 +471,15 @@ __global__ void __launch_bounds__(kEmitThreads, 4) k_emit(const uint2 *__restric
 }
 
 void launch_project(gs_context *c, const FrameParams *fp, const FrameBufs &b, cudaStream_t stream) {
-  uint64_t blocks = ((uint64_t)c->n + 255) / 256;
+  uint64_t blocks = ((uint64_t)c->cap + 255) / 256;
   const uint64_t cap = (uint64_t)c->sm_count * 16;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
-  k_project<<<(int)blocks, 256, 0, stream>>>(c->center_scale, c->cov_color, c->depth, c->n, fp, b.proj_rec, b.rect);
+  k_project<<<(int)blocks, 256, 0, stream>>>(c->center_scale, c->cov_color, c->depth, fp, b.proj_rec, b.rect);
 }
 
 void launch_emit(gs_context *c, const FrameParams *fp, FrameCounters *ctr, const FrameBufs &b, cudaStream_t st) {
-  uint64_t tiles = ((uint64_t)c->n + kEmitTile - 1) / kEmitTile;
+  uint64_t tiles = ((uint64_t)c->cap + kEmitTile - 1) / kEmitTile;
   const uint64_t cap = (uint64_t)c->sm_count * 8;
   if (tiles > cap) tiles = cap;
   if (tiles < 1) tiles = 1;

@@ -48,9 +48,10 @@ __device__ __forceinline__ DepthRange load_depth_range(const FrameCounters *ctr)
 // K1: depth + cull + min/max (index.js:517-555).  Reads 16 B + 4 B per splat, writes 4 B.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_depth_cull(const float4 *__restrict__ cs, const float *__restrict__ sa,
-                                                    uint32_t n, const FrameParams *__restrict__ fp,
+                                                    const FrameParams *__restrict__ fp,
                                                     float *__restrict__ depth_out, FrameCounters *ctr) {
   const SortConsts sc = fp->sc;
+  const uint32_t n = fp->n_splats;  // resident splats when the frame was submitted (a push may be appending more)
   double dmin = INFINITY, dmax = -INFINITY;
   uint32_t cnt = 0;
   const uint32_t stride = gridDim.x * blockDim.x;
@@ -130,7 +131,7 @@ struct RadixArgs {
   uint32_t *table;   // [256][stride]
   uint32_t *totals;  // [256]
   uint32_t stride;
-  uint32_t n_host;   // D1: number of resident splats
+  const FrameParams *fp;  // D1: fp->n_splats = number of resident splats of this frame
   // depth passes
   const float *depth;
   uint32_t *idx_a;
@@ -149,7 +150,7 @@ struct RadixArgs {
 template <int PASS>
 __device__ __forceinline__ uint32_t pass_n(const RadixArgs &a) {
   const FrameCounters *ctr = a.ctr;
-  if (PASS == PASS_D1) return ctr->sort.n_valid ? a.n_host : 0u;
+  if (PASS == PASS_D1) return ctr->sort.n_valid ? a.fp->n_splats : 0u;
   if (PASS == PASS_D2) return ctr->sort.n_inrange;
   if (PASS == PASS_T1) return ctr->overflow ? 0u : (uint32_t)ctr->n_inst;
   return ctr->overflow ? 0u : ctr->n_inst_kept;
@@ -422,14 +423,16 @@ static int persistent_grid(gs_context *c, uint64_t n_elems, int per_cta, int cta
 }
 
 void launch_depth_cull(gs_context *c, const FrameParams *fp, FrameCounters *ctr, cudaStream_t st) {
-  const int grid = persistent_grid(c, c->n, 256 * 4, 8);
-  k_depth_cull<<<grid, 256, 0, st>>>(c->center_scale, c->size_alpha, c->n, fp, c->depth, ctr);
+  // grids are sized by the table CAPACITY (stable across pushes) and the kernels read the splat count from fp, so a
+  // captured frame graph stays valid while a scene is still loading
+  const int grid = persistent_grid(c, c->cap, 256 * 4, 8);
+  k_depth_cull<<<grid, 256, 0, st>>>(c->center_scale, c->size_alpha, fp, c->depth, ctr);
 }
 
-static RadixArgs make_args(gs_context *c, FrameCounters *ctr, const FrameBufs &b) {
+static RadixArgs make_args(gs_context *c, const FrameParams *fp, FrameCounters *ctr, const FrameBufs &b) {
   RadixArgs a{};
   a.ctr = ctr;
-  a.n_host = c->n;
+  a.fp = fp;
   a.depth = c->depth;
   a.idx_a = c->idx_a;
   a.dig_a = c->dig_a;
@@ -453,19 +456,19 @@ static void run_pass(gs_context *c, RadixArgs &a, uint64_t n_max, cudaStream_t s
 }
 
 // index.js:557-567 as two stable 8-bit passes -> b.order (6 launches)
-void launch_depth_radix(gs_context *c, FrameCounters *ctr, const FrameBufs &b, cudaStream_t st) {
-  RadixArgs a = make_args(c, ctr, b);
+void launch_depth_radix(gs_context *c, const FrameParams *fp, FrameCounters *ctr, const FrameBufs &b, cudaStream_t st) {
+  RadixArgs a = make_args(c, fp, ctr, b);
   a.table = c->table_n;
   a.totals = c->totals;
   a.stride = c->table_n_stride;
-  run_pass<PASS_D1>(c, a, c->n, st);
-  run_pass<PASS_D2>(c, a, c->n, st);
+  run_pass<PASS_D1>(c, a, c->cap, st);
+  run_pass<PASS_D2>(c, a, c->cap, st);
 }
 
 // stable sort of the tile instances by tile id (5 launches: T1's histogram is produced by k_emit);
 // T2 writes the per-tile record lists
 void launch_tile_radix(gs_context *c, FrameCounters *ctr, const FrameBufs &b, cudaStream_t st) {
-  RadixArgs a = make_args(c, ctr, b);
+  RadixArgs a = make_args(c, nullptr, ctr, b);
   a.table = c->table_d;
   a.totals = c->totals + 256;
   a.stride = c->table_d_stride;

@@ -62,6 +62,10 @@ class SplatContext:
     def clear(self) -> None:
         self._check(self._lib.gs_clear(self._h))
 
+    def reserve(self, n_total: int) -> None:
+        """gs_reserve: size the table for n_total splats (initGL(numVertexes), index.js:248-251)."""
+        self._check(self._lib.gs_reserve(self._h, int(n_total)))
+
     def push_splats(self, rows: np.ndarray) -> None:
         """rows: (n, 32) uint8 raw .splat rows (pushDataBuffer, index.js:328)."""
         rows = np.ascontiguousarray(rows, dtype=np.uint8).reshape(-1, 32)
@@ -137,6 +141,27 @@ class SplatContext:
         self._check(self._lib.gs_render(self._h, C.byref(p), _ptr(out), C.byref(st)))
         self.last_stats = st
         return out
+
+    def render_stereo(self, view: np.ndarray, eyes, cutout: Optional[np.ndarray] = None, bg=(0.0, 0.0, 0.0, 0.0),
+                      fmt: int = GS_FORMAT_RGBA8):
+        """gs_render_stereo: one sort with the head camera's `view` (+ cutout), one draw per eye (two FrameInputs).
+        Returns the two frames, row 0 = bottom."""
+        assert len(eyes) == 2
+        dtype = np.uint8 if fmt == GS_FORMAT_RGBA8 else np.float32
+        outs = [np.empty((e.height, e.width, 4), dtype) for e in eyes]
+        arr = (GsRenderParams * 2)()
+        keep = [self.make_params(e, bg, fmt, 0) for e in eyes]
+        for i in range(2):
+            C.memmove(C.addressof(arr[i]), C.addressof(keep[i]), C.sizeof(GsRenderParams))
+        ptrs = (C.c_void_p * 2)(outs[0].ctypes.data, outs[1].ctypes.data)
+        stats = (GsStats * 2)()
+        v = np.ascontiguousarray(view, dtype=np.float32).reshape(4)
+        cu = None if cutout is None else np.ascontiguousarray(cutout, dtype=np.float32).reshape(16)
+        self._check(self._lib.gs_render_stereo(self._h, v.ctypes.data_as(C.POINTER(C.c_float)),
+                                               None if cu is None else cu.ctypes.data_as(C.POINTER(C.c_float)),
+                                               arr, ptrs, stats))
+        self.last_stereo_stats = [stats[0], stats[1]]
+        return outs
 
     def render_raw(self, params: GsRenderParams, out_ptr: int) -> GsStats:
         """gs_render with a caller-provided pointer (device pointer when GS_RENDER_OUT_DEVICE is set)."""

@@ -114,6 +114,17 @@ GS_API int gs_clear(gs_context *ctx);
  * (index.js:343-402, fp64, incl. the parseInt quirk) runs on the device.  rows32 is host memory.
  */
 GS_API int gs_push_splats(gs_context *ctx, const void *rows32, uint32_t n);
+/*
+ * Progressive loading (index.js:259-298: rows are pushed as they arrive while the scene is already being drawn):
+ * gs_push_splats / gs_push_packed do NOT wait for frames in flight.  A frame draws the splats that were resident when
+ * it was submitted; the pushed rows are staged through page-locked buffers and packed on a separate stream behind it,
+ * and the next submitted frame sees them.  rows32 is fully consumed when the call returns.  The only push that waits
+ * for the pipeline is one that outgrows the table's capacity (geometric growth) - never after gs_reserve.
+ *
+ * gs_reserve: size the resident table for n_total splats up front, what initGL(numVertexes) does with the
+ * Content-Length (index.js:248-251, 26-46).
+ */
+GS_API int gs_reserve(gs_context *ctx, uint32_t n_total);
 
 /*
  * Append n already-packed splats: the two data-texture records the reference uploads
@@ -184,6 +195,16 @@ GS_API int gs_render(gs_context *ctx, const gs_render_params *params, void *out_
  */
 GS_API int gs_render_async(gs_context *ctx, const gs_render_params *params, void *out_rgba, uint64_t *out_ticket);
 GS_API int gs_wait(gs_context *ctx, uint64_t ticket, gs_stats *stats);
+
+/*
+ * WebXR / stereo (index.js:13-15 xrPixelRatio, 184-195): the scene's one sort request per frame comes from the HEAD
+ * camera (tick(), index.js:438-455: `view` = row 2 of its gsModelViewMatrix, plus the cutout), while the mesh is drawn
+ * once per EYE with that eye's matrices and viewport (material.onBeforeRender runs per eye camera).  gs_render_stereo =
+ * one gs_sort + two draws with that order; eyes[e].has_cutout / cutout16 are ignored (the cutout acts in the sort).
+ * stats2_or_null, when given, receives the two eyes' stats.
+ */
+GS_API int gs_render_stereo(gs_context *ctx, const float view[4], const float *cutout16_or_null,
+                            const gs_render_params eyes[2], void *const out_rgba[2], gs_stats *stats2_or_null);
 
 /* Per-splat projected record of the last gs_render (testing the vertex-shader restatement):
  * 8 floats per resident splat {cx, cy, a1x, a1y, a2x, a2y, rgba8-as-bits, tile-rect-as-bits};

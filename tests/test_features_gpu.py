@@ -123,3 +123,105 @@ def test_stats_frame_counts(gs, orc, ctx):
     assert st["n_records_streamed"] >= st["n_tile_instances"]
     assert 0 < st["n_pair_hits"] <= st["n_pair_tests"]
     assert st["n_pair_hits"] <= pairs * 1.001 + 16                     # early-stopped pixels skip pairs, never add any
+
+
+def _eye_cameras(gs, w, h, ipd=0.064):
+    """Two eye cameras around the fixed head camera (same orientation, +-ipd/2 along x)."""
+    tm = gs.three_math
+    head = gs.scenes.fixed_camera(w, h)
+    eyes = []
+    for sx in (-0.5, 0.5):
+        eyes.append(tm.PerspectiveCamera(fov=80.0, aspect=w / h, near=0.005, far=10000.0,
+                                         position=(head.position[0] + sx * ipd, head.position[1], head.position[2])))
+    return head, eyes
+
+
+def test_stereo_one_sort_two_eyes(gs, orc, ctx):
+    """gs_render_stereo (index.js:184-195 per-eye onBeforeRender + one tick() sort): both eyes are drawn with the HEAD
+    camera's order; each eye frame equals the oracle's frame for (head order, eye matrices)."""
+    w, h = 640, 400
+    rows, cs, cc, m, fr_head = scene_inputs(gs, orc, 60000, 2024, w, h)
+    ctx.clear(); ctx.push_packed(cs, cc, m[:, 15])
+    sc = gs.scenes
+    head, eye_cams = _eye_cameras(gs, w, h)
+    fr_head = sc.make_frame(head, sc.demo_object(), w, h)
+    eyes = [sc.make_frame(c, sc.demo_object(), w, h) for c in eye_cams]
+    order = orc.sort(m, fr_head.view)
+    got = ctx.render_stereo(fr_head.view, eyes, fmt=gs.GS_FORMAT_RGBA32F, bg=(0.0, 0.1, 0.2, 1.0))
+    for e, g in zip(eyes, got):
+        exp, _ = orc.render(cs, cc, order, e.proj, e.modelview, w, h, e.focal, bg=(0.0, 0.1, 0.2, 1.0))
+        assert np.abs(g - exp).max() <= FRAME_TOL
+    assert not np.array_equal(got[0], got[1])
+    st = ctx.last_stereo_stats
+    assert st[0].n_sorted == st[1].n_sorted == len(order) and st[0].ms_sort > 0 and st[1].ms_sort == 0
+    # with a cutout the cull acts in the one sort
+    cut_fr = sc.make_frame(head, sc.demo_object(), w, h, sc.demo_cutout())
+    order_c = orc.sort(m, cut_fr.view, cut_fr.cutout)
+    got = ctx.render_stereo(cut_fr.view, eyes, cutout=cut_fr.cutout, fmt=gs.GS_FORMAT_RGBA32F)
+    exp, _ = orc.render(cs, cc, order_c, eyes[1].proj, eyes[1].modelview, w, h, eyes[1].focal)
+    assert len(order_c) < len(order) and np.abs(got[1] - exp).max() <= FRAME_TOL
+
+
+def test_component_render_xr(gs, orc):
+    """The component mirror: xrPixelRatio scales the eye viewports (index.js:13-15), tick()'s camera sorts."""
+    sc = gs.scenes
+    rows = gs.synth_splats(30000, 11)
+    cs, cc, m = orc.pack(rows)
+    w, h = 800, 450
+    head, eye_cams = _eye_cameras(gs, w, h)
+    comp = gs.GaussianSplattingComponent({"src": rows.tobytes(), "xrPixelRatio": 0.5})
+    comp.init(head, sc.demo_object())
+    try:
+        left, right = comp.render_xr(eye_cams, w, h, fmt=gs.GS_FORMAT_RGBA32F)
+        assert left.shape == (225, 400, 4) and right.shape == (225, 400, 4)
+        fr_head = sc.make_frame(head, sc.demo_object(), 400, 225)
+        order = orc.sort(m, fr_head.view)
+        e = sc.make_frame(eye_cams[0], sc.demo_object(), 400, 225)
+        exp, _ = orc.render(cs, cc, order, e.proj, e.modelview, 400, 225, e.focal)
+        assert np.abs(left - exp).max() <= FRAME_TOL
+    finally:
+        comp.renderer.close()
+
+
+def test_progressive_push_while_rendering(gs, orc):
+    """index.js:259-298: rows are pushed as they arrive while the scene is drawn.  Pushes are interleaved with
+    gs_render_async; every frame must equal the oracle's frame of the prefix that was resident when it was submitted."""
+    w, h = 640, 360
+    n, chunk = 240000, 40000
+    rows = gs.synth_splats(n, 555)
+    cs, cc, m = orc.pack(rows)
+    sc = gs.scenes
+    fr = sc.make_frame(sc.fixed_camera(w, h), sc.demo_object(), w, h)
+    with gs.SplatContext(0) as c:
+        c.reserve(n)  # initGL(numVertexes): no growth (hence no pipeline wait) during the load
+        outs, tickets, prefixes = [], [], []
+        for first in range(0, n, chunk):
+            c.push_splats(rows[first:first + chunk])
+            out = c.pinned_array((h, w, 4), np.float32)
+            out[...] = -1.0
+            t = c.render_async(c.make_params(fr, fmt=gs.GS_FORMAT_RGBA32F), out.ctypes.data)
+            outs.append(out); tickets.append(t); prefixes.append(first + chunk)
+            if len(tickets) >= 3:  # keep three frames in flight across the pushes
+                st = c.wait(tickets[-3])
+                assert st.n_splats == prefixes[-3]
+        for t, k in zip(tickets[-2:], prefixes[-2:]):
+            assert c.wait(t).n_splats == k
+        for out, k in zip(outs, prefixes):
+            order = orc.sort(m[:k], fr.view)
+            exp, _ = orc.render(cs[:k], cc[:k], order, fr.proj, fr.modelview, w, h, fr.focal)
+            assert np.abs(out - exp).max() <= FRAME_TOL, k
+        assert c.num_splats == n
+        # without gs_reserve the table grows geometrically; frames stay correct across the growth
+    with gs.SplatContext(0) as c:
+        outs, tickets, prefixes = [], [], []
+        for first in range(0, n, chunk):
+            c.push_splats(rows[first:first + chunk])
+            out = np.empty((h, w, 4), np.float32)
+            tickets.append(c.render_async(c.make_params(fr, fmt=gs.GS_FORMAT_RGBA32F), out.ctypes.data))
+            outs.append(out); prefixes.append(first + chunk)
+        for t in tickets[-3:]:
+            c.wait(t)
+        for out, k in zip(outs[::2], prefixes[::2]):
+            order = orc.sort(m[:k], fr.view)
+            exp, _ = orc.render(cs[:k], cc[:k], order, fr.proj, fr.modelview, w, h, fr.focal)
+            assert np.abs(out - exp).max() <= FRAME_TOL, k
