@@ -113,18 +113,25 @@ __device__ __forceinline__ void store_pixel(const FrameParams *fp, uint32_t tile
   }
 }
 
+#ifndef GS_RASTER_STAGES
+#define GS_RASTER_STAGES 4   // TMA ring depth of the packed kernel
+#endif
+#ifndef GS_RASTER_MINB
+#define GS_RASTER_MINB 8     // resident CTAs per SM the packed kernel is compiled for (register budget 65536 / (128 * MINB))
+#endif
 template <bool PACKED>
 struct RasterCfg {
   static constexpr int kThreads = PACKED ? 128 : 256;
   static constexpr int kChunk = PACKED ? 128 : 256;   // records per TMA bulk copy == one cull pass (one record per thread)
-  static constexpr int kStages = PACKED ? 4 : 3;       // ring depth
+  static constexpr int kStages = PACKED ? GS_RASTER_STAGES : 3;  // ring depth
   static constexpr int kCv = PACKED ? 5 : 3;           // float4 per converted record
+  static constexpr int kMinBlocks = PACKED ? GS_RASTER_MINB : 4;
 };
 
 // DEPTH: depth-test every fragment LEQUAL against fp->depth_in (index.js:179-180).  STATS: count what the tile does
 // (and keep culling the whole list after the tile has closed, so that the count of 16x16 tile instances is exact).
 template <bool PACKED, bool DEPTH, bool STATS>
-__global__ void __launch_bounds__(RasterCfg<PACKED>::kThreads) k_raster(const float4 *__restrict__ inst_rec,
+__global__ void __launch_bounds__(RasterCfg<PACKED>::kThreads, RasterCfg<PACKED>::kMinBlocks) k_raster(const float4 *__restrict__ inst_rec,
                                                                         const uint2 *__restrict__ bin_range,
                                                                         const FrameParams *__restrict__ fp,
                                                                         uint4 *__restrict__ tile_stats) {

@@ -88,6 +88,12 @@ class TileSharding:
         return frame
 
 
+def rank_frame(step: int, rank: int, world: int) -> int:
+    """Frame-parallel mode: index in the frame stream of the frame `rank` renders at its local step `step`
+    (rank r takes frames r, r + world, r + 2*world, ...: whole frames are the independent units, no exchange)."""
+    return step * world + rank
+
+
 class ShardedRenderer:
     """One rank of a frame-sharded render.
 

@@ -72,9 +72,21 @@ def algorithmic_bytes(st: dict) -> dict:
     }
 
 
-def parallelism_label(world: int, exchange: str) -> str:
+def parallel_mode(args) -> str:
+    """How N > 1 GPUs are used.  `frames`: every rank holds the whole scene and renders every N-th frame of the stream
+    (independent units, no data-path collective, weak scaling: the north star shards the splats "only when the scene
+    outgrows one GPU").  `tiles`: ONE frame is sharded by screen bin columns over the ranks and the finished tiles are
+    exchanged (strong scaling; the default for the 80 M-splat configuration)."""
+    if args.parallel != "auto":
+        return args.parallel
+    return "tiles" if args.workload == "synth_80m_1080p" else "frames"
+
+
+def parallelism_label(world: int, exchange: str, mode: str = "tiles") -> str:
     if world == 1:
         return "1 GPU"
+    if mode == "frames":
+        return f"frame-parallel x{world}: every rank renders every {world}-th frame of the stream from its own replica of the splat table, no data-path collective"
     if exchange == "p2p":
         return f"screen-tile-column sharding x{world}, raster fused with the exchange over NVLink peer memory"
     return f"screen-tile-column sharding x{world} + NCCL all-gather of RGBA8 tiles"
@@ -83,7 +95,7 @@ def parallelism_label(world: int, exchange: str) -> str:
 def config_block(args, workload: str, n: int, w: int, h: int, orbit: bool) -> dict:
     """The `config` object: IDENTICAL in both arms for the same command line (the driver compares them)."""
     return {"workload": workload, "n_splats": n, "width": w, "height": h, "camera": "orbit-120" if orbit else "fixed",
-            "parallelism": parallelism_label(args.gpus, args.exchange),
+            "parallelism": parallelism_label(args.gpus, args.exchange, parallel_mode(args)),
             "l2": "GPU arm: flushed between timed steps (160 MiB memset on the raster stream, INSIDE the timed region)"}
 
 
@@ -201,7 +213,8 @@ def run_reference(args):
               + ("full frames" if band == (0, h) else f"rows {band[0]}..{band[1]} of {h} shaded per step, raster time scaled by {h}/{band[1]-band[0]}")
               + "; value = 1 / median step")
     line = {"impl": "reference", "metric": METRICS.get(args.workload, METRIC), "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak" if (args.gpus > 1 and parallel_mode(args) == "frames") else "strong",
             "vs_baseline": None, "dtype": DTYPE, "data": "synthetic",
             "config": config_block(args, args.workload, n, w, h, len(frames) > 1),
             "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port", "sample": sample,
@@ -299,7 +312,9 @@ def run_ours(args):
     os.environ.setdefault("GS_BENCH", "1")
     uuid = str(torch.cuda.get_device_properties(dev).uuid)
     uuid = uuid if uuid.startswith("GPU-") else "GPU-" + uuid
-    sharded = world > 1
+    mode = parallel_mode(args)
+    sharded = world > 1 and mode == "tiles"   # one frame split over the ranks
+    afr = world > 1 and mode == "frames"      # whole frames dealt round-robin to the ranks
     peak, peak_src = load_peaks()
 
     def barrier():
@@ -322,11 +337,15 @@ def run_ours(args):
         ctx.clear()
         if sharded:
             ctx.set_shard(rank, world)
-        t0 = time.perf_counter()
         chunk = 4 << 20
+        ctx.reserve(n)                      # initGL(numVertexes): size the table once (index.js:248-251)
+        ctx.push_splats(rows[:min(n, 1 << 18)])  # first touch of the staging buffers is not part of the rate
+        ctx.read_packed(0, 1)               # (waits for the push stream)
+        ctx.clear()
+        t0 = time.perf_counter()
         for first in range(0, n, chunk):
             ctx.push_splats(rows[first:first + chunk])
-        ctx.synchronize()
+        ctx.read_packed(0, 1)
         t_push = time.perf_counter() - t0
         tiles_per_rank = max(ctx.owned_tiles(w, h, r, world) for r in range(world))
         flags = gs.GS_RENDER_OUT_DEVICE | (gs.GS_RENDER_OUT_TILED if sharded else 0)
@@ -359,12 +378,16 @@ def run_ours(args):
             peer_dev = ctx.make_params(fr, fmt=gs.GS_FORMAT_RGBA8, flags=gs.GS_RENDER_OUT_DEVICE | gs.GS_RENDER_OUT_PEER)
             peer_host = ctx.make_params(fr, fmt=gs.GS_FORMAT_RGBA8, flags=gs.GS_RENDER_OUT_PEER)
 
+        def fidx(i):
+            """frame of the stream this rank renders at its step i (frame-parallel: rank r takes frames r, r+N, ...)"""
+            return (gs.dist.rank_frame(i, rank, world) if afr else i) % nf
+
         def submit_device(i):
             """enqueue frame i on the library's streams (no host synchronisation); returns its ticket"""
             if use_peer:
                 return ctx.render_async(peer_dev, 1)  # the assembled frame lands in the shared ring
             if not sharded:
-                return ctx.render_async(p_dev[i % nf], frames_dev[i % 3].data_ptr())
+                return ctx.render_async(p_dev[fidx(i)], frames_dev[i % 3].data_ptr())
             t = ctx.render_async(p_dev[i % nf], tiles_bufs[i % 3].data_ptr())
             with torch.cuda.stream(stream):
                 dist.all_gather_into_tensor(gath_bufs[i % 3], tiles_bufs[i % 3])
@@ -402,8 +425,9 @@ def run_ours(args):
         barrier()
         total_ms = allmax(run_pipeline(submit_device, steps))
         barrier()
+        units = world if afr else 1  # frames finished per step across the job
         ms_per_step = total_ms / steps
-        fps = 1000.0 / ms_per_step
+        fps = units * 1000.0 / ms_per_step
 
         # ---- un-overlapped frames (one in flight) for the per-stage / roofline numbers: with three frames in flight the
         #      stages of consecutive frames run concurrently and their individual durations stretch ----
@@ -421,7 +445,7 @@ def run_ours(args):
         host_frames = [ctx.pinned_array((h, w, 4), np.uint8) for _ in range(3)]
         if not sharded:
             def submit_host(i):
-                return ctx.render_async(p_host[i % nf], host_frames[i % 3].ctypes.data)
+                return ctx.render_async(p_host[fidx(i)], host_frames[i % 3].ctypes.data)
         elif use_peer:
             def submit_host(i):
                 return ctx.render_async(peer_host, host_frames[i % 3].ctypes.data)
@@ -435,8 +459,8 @@ def run_ours(args):
         barrier()
         e2e_ms = allmax(run_pipeline(submit_host, steps)) / steps
         barrier()
-        e2e = {"value": 1000.0 / e2e_ms, "unit": "frames/s", "ms_per_step": e2e_ms,
-               "h2d_bytes_per_step": C.sizeof(gs.GsRenderParams), "d2h_bytes_per_step": h * w * 4,
+        e2e = {"value": units * 1000.0 / e2e_ms, "unit": "frames/s", "ms_per_step": e2e_ms,
+               "h2d_bytes_per_step": units * C.sizeof(gs.GsRenderParams), "d2h_bytes_per_step": units * h * w * 4,
                "note": "gs_render_async/gs_wait with host buffers, three frames in flight: the camera matrices go in as one small "
                        "H2D copy, the RGBA8 frame comes back to pinned host memory on a copy stream while the next frame renders; "
                        "the timed region (one CUDA-event pair around all K steps) includes every copy and the L2 flushes"}
@@ -467,6 +491,15 @@ def run_ours(args):
                 d = np.abs(got.astype(np.int32) - ref.astype(np.int32))
                 frame_check = "bit-identical" if int(d.max()) == 0 else f"differs: max {int(d.max())} LSB on {int((d > 0).sum())} channel values"
             barrier()
+
+        if afr:  # every rank renders the SAME reference frame: the pictures must agree bit for bit across the ranks
+            ref = ctx.render(fr, fmt=gs.GS_FORMAT_RGBA8)
+            hsh = int.from_bytes(__import__("hashlib").sha256(ref.tobytes()).digest()[:7], "little")
+            t = torch.tensor([hsh], device=dev, dtype=torch.int64)
+            lst = [torch.zeros_like(t) for _ in range(world)]
+            dist.all_gather(lst, t)
+            same = all(int(x.item()) == hsh for x in lst)
+            frame_check = "bit-identical" if same else "differs: the ranks' frames of the same camera have different hashes"
 
         res = None
         if rank == 0:
@@ -506,7 +539,7 @@ def run_ours(args):
                                          "that walks every bin list to its end (a timed frame stops a tile once its pixels are saturated)"},
                 "msplats_per_s": n * fps / 1e6,
                 "e2e": e2e,
-                "gpu_launches": (int(st["kernel_launches"]) + (2 if use_peer else (1 if sharded else 0))) * steps,
+                "gpu_launches": (int(st["kernel_launches"]) + (2 if use_peer else (1 if sharded else 0))) * steps * units,
                 "clocks": clocks,
                 "roofline": {"kernel": kernels[dom], "bound": "hbm", "achieved": r["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": r["frac"],
                              "traffic": traffic, "peak_source": peak_src,
@@ -542,7 +575,8 @@ def run_ours(args):
     rc = 0
     if rank == 0:
         line = {"metric": head["metric"], "value": head["value"], "unit": "frames/s", "n_gpus": world, "steps": args.steps,
-                "warmup": max(args.warmup, 3), "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "strong",
+                "warmup": max(args.warmup, 3), "ms_per_step": head["ms_per_step"], "higher_is_better": True,
+                "scaling": "weak" if afr else "strong",
                 "vs_baseline": None, "dtype": DTYPE, "data": "synthetic"}
         line.update({k: v for k, v in head.items() if k not in line})
         line["pipeline"] = ("three frames in flight: frame k is rasterised (low-priority stream) while frame k+1 is binned and frame "
@@ -575,6 +609,9 @@ def main():
     ap.add_argument("--splats", type=int, default=0, help="override the workload's splat count (debug)")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the oracle legs (parity block + cpu_baseline)")
     ap.add_argument("--no-other-configs", action="store_true", help="N = 1: time only the headline configuration")
+    ap.add_argument("--parallel", default="auto", choices=["auto", "frames", "tiles"],
+                    help="N > 1: `frames` = every rank renders every N-th frame from its own replica (weak scaling, default); "
+                         "`tiles` = one frame sharded by screen bin columns + tile exchange (strong scaling, default for the 80 M scene)")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
                     help="multi-GPU frame exchange: fused raster + NVLink peer stores (default) or NCCL all-gather of tiles")
     args = ap.parse_args()

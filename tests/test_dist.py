@@ -53,6 +53,32 @@ def test_sharded_frame_gloo_world2(tmp_path):
     assert open(out).read() == "ok"
 
 
+def _afr_worker(rank, world, port, tmp):
+    import torch
+    import torch.distributed as dist
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    gs = importlib.import_module("aframe-gaussian-splatting_b200")
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    steps = 7
+    mine = torch.tensor([gs.dist.rank_frame(i, rank, world) for i in range(steps)])
+    allf = [torch.zeros_like(mine) for _ in range(world)]
+    dist.all_gather(allf, mine)
+    if rank == 0:
+        got = sorted(int(v) for t in allf for v in t)
+        open(tmp, "w").write("ok" if got == list(range(steps * world)) else "bad")
+    dist.destroy_process_group()
+
+
+def test_frame_parallel_partition_gloo_world2(tmp_path):
+    """Frame-parallel mode (bench.py --parallel frames): the ranks' frames partition the stream exactly."""
+    import torch.multiprocessing as mp
+    out = str(tmp_path / "afr.txt")
+    mp.spawn(_afr_worker, args=(2, 29700 + (os.getpid() % 2000), out), nprocs=2, join=True)
+    assert open(out).read() == "ok"
+
+
 def test_tile_sharding_arithmetic(gs):
     for world in (1, 2, 3, 8):
         sh = gs.dist.TileSharding(W, H, world)
