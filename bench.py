@@ -419,12 +419,22 @@ def run_ours(args):
             return r0.elapsed_time(r1)
 
         run_pipeline(submit_device, max(args.warmup, 3))
+        # ... and keep warming until the GPU has been busy for ~0.3 s: a freshly woken GPU (the second rank's in
+        # particular) needs longer than three 0.3 ms frames to reach its clocks.  Same count on every rank.
+        t_w = time.perf_counter()
+        run_pipeline(submit_device, 50)
+        per50 = allmax(time.perf_counter() - t_w)
+        for _ in range(int(min(40, max(0.0, 0.3 - per50) / max(per50, 1e-4)))):
+            run_pipeline(submit_device, 50)
         sampler = ClockSampler(uuid) if rank == 0 else None
 
         # ---- value: device-resident frames ----
         barrier()
-        total_ms = allmax(run_pipeline(submit_device, steps))
+        my_ms = run_pipeline(submit_device, steps)
+        total_ms = allmax(my_ms)
         barrier()
+        if world > 1:
+            sys.stderr.write(f"[bench] rank {rank}: {my_ms / steps:.4f} ms per step (max over ranks {total_ms / steps:.4f})\n")
         units = world if afr else 1  # frames finished per step across the job
         ms_per_step = total_ms / steps
         fps = units * 1000.0 / ms_per_step
