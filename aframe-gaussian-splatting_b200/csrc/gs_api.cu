@@ -145,6 +145,27 @@ static int ensure_tile_stats(gs_context *c, uint32_t n_tiles) {
   return GS_OK;
 }
 
+// buffers of the front-to-back slab path (gs_slab.cu); the pipeline is idle when this runs
+static int ensure_slab(gs_context *c, uint32_t n_tiles, uint32_t n_bins) {
+  if (c->slab_cap < c->cap || !c->key32) {
+    dev_free(c->key32); dev_free(c->cidx); dev_free(c->ckey); dev_free(c->chunk_cnt);
+    GS_CUDA(c, dev_alloc(&c->key32, (size_t)c->cap + 8));
+    GS_CUDA(c, dev_alloc(&c->cidx, (size_t)c->cap));
+    GS_CUDA(c, dev_alloc(&c->ckey, (size_t)c->cap));
+    GS_CUDA(c, dev_alloc(&c->chunk_cnt, (size_t)c->cap / 2048 + 4));
+    c->slab_cap = c->cap;
+  }
+  if (!c->slab_tab) GS_CUDA(c, dev_alloc(&c->slab_tab, 1));
+  if (c->slab_tiles_cap < n_tiles || !c->pix_state) {
+    dev_free(c->pix_state); dev_free(c->tile_closed); dev_free(c->bin_open);
+    GS_CUDA(c, dev_alloc(&c->pix_state, (size_t)n_tiles * 256));
+    GS_CUDA(c, dev_alloc(&c->tile_closed, (size_t)n_tiles));
+    GS_CUDA(c, dev_alloc(&c->bin_open, (size_t)n_bins));  // bins <= tiles
+    c->slab_tiles_cap = n_tiles;
+  }
+  return GS_OK;
+}
+
 static int ensure_frame(gs_context *c, gs_context::Slot &sl, size_t bytes) {
   if (bytes <= sl.frame_bytes && sl.frame_dev) return GS_OK;
   if (sl.frame_dev) cudaFree(sl.frame_dev);
@@ -238,6 +259,10 @@ extern "C" int gs_create(int device_ordinal, gs_context **out_ctx) {
   }
   if ((e = cudaMalloc((void **)&c->sort_hdr, sizeof(SortHeader))) != cudaSuccess) return bail("cudaMalloc", e);
   c->use_graphs = getenv("GS_NO_GRAPH") == nullptr;
+  // scenes of at least GS_SLAB_MIN resident splats (default 4 M) are rendered front to back in depth slabs (gs_slab.cu);
+  // GS_SLAB_FIRST = target entry count of the nearest slab (default 1 M, the following ones double)
+  if (const char *e = getenv("GS_SLAB_MIN")) c->slab_min = (uint32_t)strtoull(e, nullptr, 10);
+  if (const char *e = getenv("GS_SLAB_FIRST")) c->slab_first = std::max<uint32_t>(1024u, (uint32_t)strtoull(e, nullptr, 10));
   {  // pixel loop of the raster: packed fp32x2 (default) or scalar (GS_RASTER=scalar); both give identical frames
     const char *rk = getenv("GS_RASTER");
     c->raster_base_flags = (rk && strcmp(rk, "scalar") == 0) ? 0u : 1u;
@@ -287,6 +312,8 @@ extern "C" int gs_destroy(gs_context *c) {
   if (c->peer_local) cudaFree(c->peer_local);
   dev_free(c->table_n); dev_free(c->table_d); dev_free(c->slice_total); dev_free(c->totals); dev_free(c->sort_hdr);
   dev_free(c->slice_prefix); dev_free(c->ent); dev_free(c->ent_off);
+  dev_free(c->key32); dev_free(c->cidx); dev_free(c->ckey); dev_free(c->chunk_cnt); dev_free(c->slab_tab);
+  dev_free(c->pix_state); dev_free(c->tile_closed); dev_free(c->bin_open);
   for (auto &sl : c->slot) {
     dev_free(sl.ctr); dev_free(sl.fp);
     if (sl.frame_dev) cudaFree(sl.frame_dev);
@@ -300,6 +327,9 @@ extern "C" int gs_destroy(gs_context *c) {
     if (sl.ev_sorted) cudaEventDestroy(sl.ev_sorted);
     if (sl.ev_r0) cudaEventDestroy(sl.ev_r0);
     if (sl.ev_copied) cudaEventDestroy(sl.ev_copied);
+    for (auto &pr : sl.slab_ev)
+      for (auto &ev : pr)
+        if (ev) cudaEventDestroy(ev);
   }
   for (auto &ev : c->ev)
     if (ev) cudaEventDestroy(ev);
@@ -631,6 +661,56 @@ static int launch_frame(gs_context *c, gs_context::Slot &sl, bool reuse, uint32_
   return GS_OK;
 }
 
+// Front-to-back slab path (gs_slab.cu): the whole frame is one chain on the raster stream - its kernels are large (the
+// path is for scenes of millions of splats) and every slab depends on the tiles the previous one closed.
+static int launch_frame_slabs(gs_context *c, gs_context::Slot &sl, uint32_t n_tiles, uint32_t n_bins) {
+  cudaStream_t st = c->rstream;
+  const FrameBufs b = slot_bufs(c, sl);
+  const int set = sl.set;
+  if (c->sort_set_free[set]) GS_CUDA(c, cudaStreamWaitEvent(st, c->sort_set_free[set], 0));
+  if (c->bin_set_free[set]) GS_CUDA(c, cudaStreamWaitEvent(st, c->bin_set_free[set], 0));
+  if (c->pushed) GS_CUDA(c, cudaStreamWaitEvent(st, c->push_done, 0));
+  GS_CUDA(c, cudaMemcpyAsync(sl.fp, sl.fp_host, sizeof(FrameParams), cudaMemcpyHostToDevice, st));
+  GS_CUDA(c, cudaMemsetAsync(sl.ctr, 0, sizeof(FrameCounters), st));
+  GS_CUDA(c, cudaEventRecord(sl.ev[0], st));
+  launch_depth_cull(c, sl.fp, sl.ctr, st);
+  launch_keys(c, sl.fp, sl.ctr, st);
+  // slabs of slab_first, 2x, 4x ... entries: enough of them to cover every resident splat
+  int n_slabs = 1;
+  while (n_slabs < kMaxSlabs && (uint64_t)c->slab_first * ((1ull << n_slabs) - 1ull) < sl.n_splats) ++n_slabs;
+  sl.n_slabs = n_slabs;
+  launch_slab_plan(c, sl.fp, sl.ctr, c->slab_first, n_slabs, st);
+  GS_CUDA(c, cudaEventRecord(sl.ev[1], st));
+  GS_CUDA(c, cudaEventRecord(sl.ev[2], st));
+  for (int s = 0; s < n_slabs; ++s) {
+    launch_slab_begin(c, sl.fp, sl.ctr, s, st);           // entry count (0 once every bin is closed) + compaction
+    launch_slab_sort(c, sl.fp, sl.ctr, b, st);            // draw order of the slab
+    launch_project_entries(c, sl.fp, sl.ctr, b, st);      // vertex shader for the slab's entries
+    GS_CUDA(c, cudaMemsetAsync(b.bin_range, 0, sizeof(uint2) * (size_t)n_bins, st));
+    launch_emit_slab(c, sl.fp, sl.ctr, b, st);
+    launch_tile_radix(c, sl.ctr, b, st);
+    launch_tile_ranges(c, sl.ctr, b, st);
+    for (int k = 0; k < 2; ++k)
+      if (!sl.slab_ev[s][k]) GS_CUDA(c, cudaEventCreate(&sl.slab_ev[s][k]));
+    GS_CUDA(c, cudaEventRecord(sl.slab_ev[s][0], st));
+    launch_raster_slab(c, sl.fp, sl.ctr, n_tiles, b, (sl.raster_flags & 2u) != 0, st);
+    GS_CUDA(c, cudaEventRecord(sl.slab_ev[s][1], st));
+  }
+  launch_slab_end(c, sl.ctr, st);
+  GS_CUDA(c, cudaEventRecord(sl.ev[3], st));
+  if (sl.peer) launch_peer_acquire(c, sl.fp, sl.ctr, st);
+  GS_CUDA(c, cudaEventRecord(sl.ev_r0, st));
+  launch_resolve(c, sl.fp, n_tiles, st);
+  GS_CUDA(c, cudaEventRecord(sl.ev[4], st));
+  if (sl.peer) launch_peer_signal_wait(c, sl.fp, sl.ctr, st);
+  GS_CUDA(c, cudaGetLastError());
+  GS_CUDA(c, cudaEventRecord(sl.ev_sorted, st));
+  GS_CUDA(c, cudaEventRecord(sl.ev_binned, st));
+  c->sort_set_free[set] = sl.ev_binned;
+  sl.launches = 4u + (uint32_t)n_slabs * 21u + 2u;
+  return GS_OK;
+}
+
 // after the frame's kernels: counters (and the frame, when the caller's buffer is host memory) go to the host on
 // the copy stream, so the next frame's kernels overlap the PCIe transfer
 static int enqueue_readback(gs_context *c, gs_context::Slot &sl) {
@@ -735,11 +815,15 @@ static int submit(gs_context *c, gs_context::Slot &sl) {
   // a frame normally takes the buffer set the previous frame did not; a frame that reuses the last sort must read
   // that sort's set, so it runs in it
   sl.set = reuse ? c->last_set : (c->last_set ^ 1);
-  if ((rcode = launch_frame(c, sl, reuse, rc.n_tiles, rc.n_bins))) return rcode;
+  if (sl.slab) {
+    if ((rcode = launch_frame_slabs(c, sl, rc.n_tiles, rc.n_bins))) return rcode;
+  } else {
+    if ((rcode = launch_frame(c, sl, reuse, rc.n_tiles, rc.n_bins))) return rcode;
+  }
   if ((rcode = enqueue_readback(c, sl))) return rcode;
   c->last_set = sl.set;
   sl.pending = true;
-  c->have_order = true;
+  c->have_order = !sl.slab;  // a slab frame leaves no complete draw order behind (GS_RENDER_REUSE_SORT then sorts again)
   return GS_OK;
 }
 
@@ -779,8 +863,9 @@ static int wait_slot(gs_context *c, gs_context::Slot &sl, gs_stats *stats) {
     GS_CUDA(c, cudaStreamSynchronize(c->rstream));
     // grow once to the measured demand (+12.5 %); a frame whose overflow flag is stale (an earlier frame's regrow
     // already made room) is simply run again
-    if (sl.ctr_host->n_inst > c->cap_inst) {
-      const uint64_t need = std::max<uint64_t>(sl.ctr_host->n_inst + sl.ctr_host->n_inst / 8, c->cap_inst + c->cap_inst / 2);
+    const uint64_t demand = sl.slab ? sl.ctr_host->n_inst_slab_max : sl.ctr_host->n_inst;
+    if (demand > c->cap_inst) {
+      const uint64_t need = std::max<uint64_t>(demand + demand / 8, c->cap_inst + c->cap_inst / 2);
       int rcode = ensure_instances(c, need);
       if (rcode) return rcode;
     }
@@ -805,9 +890,25 @@ static int wait_slot(gs_context *c, gs_context::Slot &sl, gs_stats *stats) {
   c->stats.width = sl.params.width;
   c->stats.height = sl.params.height;
   cudaEventElapsedTime(&c->stats.ms_sort, sl.ev[0], sl.ev[1]);
-  cudaEventElapsedTime(&c->stats.ms_project, sl.evp[0], sl.evp[1]);  // on the aux stream, overlapping the sort
-  cudaEventElapsedTime(&c->stats.ms_bin, sl.ev[2], sl.ev[3]);  // on the bin stream
-  cudaEventElapsedTime(&c->stats.ms_raster, sl.ev_r0, sl.ev[4]);
+  if (sl.slab) {
+    // slab path: ms_sort = depth/cull + keys + plan; ms_raster = the slabs' rasters + the resolve; ms_bin = the rest of
+    // the slab loop (compaction, per-slab sort, projection, binning)
+    float loop = 0.f, res = 0.f, rs = 0.f;
+    cudaEventElapsedTime(&loop, sl.ev[2], sl.ev[3]);
+    cudaEventElapsedTime(&res, sl.ev_r0, sl.ev[4]);
+    for (int s = 0; s < sl.n_slabs; ++s) {
+      float t = 0.f;
+      cudaEventElapsedTime(&t, sl.slab_ev[s][0], sl.slab_ev[s][1]);
+      rs += t;
+    }
+    c->stats.ms_project = 0.f;
+    c->stats.ms_raster = rs + res;
+    c->stats.ms_bin = loop - rs;
+  } else {
+    cudaEventElapsedTime(&c->stats.ms_project, sl.evp[0], sl.evp[1]);  // on the aux stream, overlapping the sort
+    cudaEventElapsedTime(&c->stats.ms_bin, sl.ev[2], sl.ev[3]);  // on the bin stream
+    cudaEventElapsedTime(&c->stats.ms_raster, sl.ev_r0, sl.ev[4]);
+  }
   cudaEventElapsedTime(&c->stats.ms_total, sl.ev[0], sl.ev[4]);
   c->order_count = sl.ctr_host->sort.n_valid;
   if (stats) *stats = c->stats;
@@ -829,8 +930,17 @@ extern "C" int gs_render_async(gs_context *c, const gs_render_params *p, void *o
   if (sl.pending && (rcode = wait_slot(c, sl, nullptr))) return rcode;  // slot reuse: its previous frame must be done
   if ((p->flags & GS_RENDER_REUSE_SORT) && c->have_order && (rcode = drain(c))) return rcode;  // runs in the last sort's buffers
   if ((p->flags & GS_RENDER_STATS) && (rcode = drain(c))) return rcode;  // the per-tile statistics buffer is not double-buffered
+  // large scenes render front to back in depth slabs; the two paths share scratch buffers, so a change drains
+  const bool slab = c->n >= c->slab_min && !(p->flags & (GS_RENDER_REUSE_SORT | GS_RENDER_STATS));
+  if ((int)slab != c->last_mode) {
+    if ((rcode = drain(c))) return rcode;
+    GS_CUDA(c, cudaStreamSynchronize(c->stream));
+    GS_CUDA(c, cudaStreamSynchronize(c->bstream));
+    GS_CUDA(c, cudaStreamSynchronize(c->rstream));
+    c->last_mode = (int)slab;
+  }
   // growing any shared buffer needs an idle pipeline
-  const bool grow = !(c->scratch_cap >= c->cap && c->depth) || !(n_bins <= c->bins_cap && c->bin_range[0]) || !(n_tiles <= c->tile_stats_cap && c->tile_stats) || c->cap_inst == 0;
+  const bool grow = (slab && (c->slab_cap < c->cap || !c->key32 || c->slab_tiles_cap < n_tiles || !c->slab_tab)) || !(c->scratch_cap >= c->cap && c->depth) || !(n_bins <= c->bins_cap && c->bin_range[0]) || !(n_tiles <= c->tile_stats_cap && c->tile_stats) || c->cap_inst == 0;
   if (grow) {
     if ((rcode = drain(c))) return rcode;
     GS_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -839,10 +949,11 @@ extern "C" int gs_render_async(gs_context *c, const gs_render_params *p, void *o
     if ((rcode = ensure_scratch(c))) return rcode;
     if ((rcode = ensure_bins(c, n_bins))) return rcode;
     if ((rcode = ensure_tile_stats(c, n_tiles))) return rcode;
+    if (slab && (rcode = ensure_slab(c, n_tiles, n_bins))) return rcode;
     if (c->cap_inst == 0) {
       // first frame: room for two bin instances per resident splat (a typical scene needs ~1); GS_INST_CAP overrides
       // the initial size (tests of the overflow / regrow path)
-      uint64_t first = std::max<uint64_t>(1u << 20, (uint64_t)c->n * 2);
+      uint64_t first = std::max<uint64_t>(1u << 20, slab ? (uint64_t)c->n : (uint64_t)c->n * 2);
       if (const char *e = getenv("GS_INST_CAP")) first = std::max<uint64_t>(1024, strtoull(e, nullptr, 10));
       if ((rcode = ensure_instances(c, first))) return rcode;
     }
@@ -851,6 +962,7 @@ extern "C" int gs_render_async(gs_context *c, const gs_render_params *p, void *o
   sl.out_user = out_rgba;
   sl.ticket = ticket;
   sl.n_splats = c->n;
+  sl.slab = slab;
   if ((rcode = submit(c, sl))) return rcode;
   c->next_ticket = ticket + 1;
   if (out_ticket) *out_ticket = ticket;

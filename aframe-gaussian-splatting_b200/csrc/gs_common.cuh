@@ -56,7 +56,15 @@ struct FrameCounters {
   uint32_t overflow;           // instance buffer too small: frame must be re-run
   uint32_t peer_timeout;       // a peer flag was not seen in time (fused exchange)
   uint32_t count_done;         // k_count CTAs finished (the last one scans the slice totals)
-  uint32_t pad;
+  // ---- front-to-back slab path (large scenes): see gs_slab.cu ----
+  uint32_t open_bins;          // bins of this rank that still have a live pixel
+  uint32_t slab_real;          // real entries of the current slab (it may also hold quirk-Q5 repeats of splat 0)
+  uint32_t total_valid;        // V and V - dropped of the whole frame (sort.n_valid / n_inrange hold the CURRENT slab's
+  uint32_t total_inrange;      //   entry count while the slab loop runs, so the sort / emit kernels work unchanged)
+  uint32_t n_kept_total;       // bin instances kept, summed over the slabs
+  uint32_t slabs_run;          // slabs that found open bins and entries
+  unsigned long long n_inst_total;  // bin-instance candidates, summed over the slabs
+  unsigned long long n_inst_slab_max;  // ... of the largest slab (what the instance buffers must hold)
 };
 static_assert(offsetof(FrameCounters, sort) == 0 && sizeof(SortHeader) == 32, "SortHeader is the prefix of FrameCounters");
 
@@ -101,6 +109,17 @@ struct FrameParams {
   unsigned long long peer_need;          // slot may be overwritten once every rank released seq >= peer_need
 };
 
+
+// ---- front-to-back slab path ----
+constexpr int kMaxSlabs = 12;          // geometric slab sizes: 1 M, 2 M, 4 M ... entries (nearest first)
+constexpr int kSlabBuckets = 4096;     // slab boundaries are chosen on a 4096-bucket histogram of the 16-bit keys
+constexpr uint32_t kNoKey = 0xFFFFFFFFu;
+struct SlabTable {
+  uint32_t hist[kSlabBuckets];  // entries per 16-key bucket
+  uint32_t klo[kMaxSlabs];      // slab s holds the keys [klo[s], khi[s])
+  uint32_t khi[kMaxSlabs];
+  uint32_t count[kMaxSlabs];    // entries of slab s
+};
 
 }  // namespace gs
 
@@ -149,6 +168,20 @@ struct gs_context {
   // ---- per-frame tables ----
   uint32_t bins_cap = 0;
   uint2 *bin_range[2] = {nullptr, nullptr};  // [bins] {start, end} into inst_rec, one per slot (read by the raster)
+  // ---- front-to-back slab path (gs_slab.cu): allocated when a scene first crosses the slab threshold ----
+  uint32_t slab_cap = 0;           // splats the per-splat slab buffers are sized for
+  uint32_t *key32 = nullptr;       // [cap] 16-bit depth key of every splat, kNoKey if not in the sort
+  uint32_t *cidx = nullptr;        // [cap] splat indices of the current slab, in index order
+  uint16_t *ckey = nullptr;        // [cap] their keys
+  uint32_t *chunk_cnt = nullptr;   // [cap / 2048 + 2] compaction offsets
+  gs::SlabTable *slab_tab = nullptr;
+  float4 *pix_state = nullptr;     // [tiles * 256] {R, G, B, T} carried from slab to slab
+  uint8_t *tile_closed = nullptr;  // [tiles]
+  uint32_t *bin_open = nullptr;    // [bins] live tiles per bin (0 for bins of other ranks)
+  uint32_t slab_tiles_cap = 0;
+  uint32_t slab_min = 4u << 20;    // scenes with at least this many resident splats render front to back in slabs
+  uint32_t slab_first = 1u << 20;  // target entry count of the nearest slab (the following ones double)
+  int last_mode = 0;               // 0 = one pass (three-stage pipeline), 1 = slab path
   uint4 *tile_stats = nullptr;     // [tiles] per-tile counts of a GS_RENDER_STATS frame
   uint4 *tile_stats_host = nullptr;  // pinned copy
   uint32_t tile_stats_cap = 0;
@@ -168,6 +201,9 @@ struct gs_context {
     size_t depth_bytes = 0;
     uint32_t raster_flags = 0;               // k_raster instantiation of this frame (packed | depth | stats)
     uint32_t n_splats = 0;                   // resident splats when the frame was submitted
+    bool slab = false;                       // rendered by the front-to-back slab path
+    int n_slabs = 0;
+    cudaEvent_t slab_ev[gs::kMaxSlabs][2] = {};  // raster of each slab (timing)
     cudaEvent_t ev[5]{};                     // stage boundaries (timing)
     cudaEvent_t evp[2]{};                    // k_project on the aux stream (timing)
     cudaEvent_t ev_done = nullptr, ev_copied = nullptr;
@@ -262,6 +298,17 @@ void launch_peer_signal_wait(gs_context *c, const FrameParams *fp, FrameCounters
 struct PeerRows { unsigned long long *p[kMaxPeers]; };
 void launch_peer_release(gs_context *c, const PeerRows &rows, uint32_t world, uint32_t rank, unsigned long long seq,
                          cudaStream_t st);
+// ---- slab path launchers (gs_slab.cu / gs_raster.cu) ----
+void launch_keys(gs_context *c, const FrameParams *fp, FrameCounters *ctr, cudaStream_t st);          // keys + bucket histogram
+void launch_slab_plan(gs_context *c, const FrameParams *fp, FrameCounters *ctr, uint32_t first_target, int n_slabs, cudaStream_t st);
+void launch_slab_begin(gs_context *c, const FrameParams *fp, FrameCounters *ctr, int slab, cudaStream_t st);  // + compaction: 4 launches
+void launch_slab_sort(gs_context *c, const FrameParams *fp, FrameCounters *ctr, const FrameBufs &b, cudaStream_t st);  // 6 launches
+void launch_project_entries(gs_context *c, const FrameParams *fp, FrameCounters *ctr, const FrameBufs &b, cudaStream_t st);
+void launch_emit_slab(gs_context *c, const FrameParams *fp, FrameCounters *ctr, const FrameBufs &b, cudaStream_t st);
+void launch_slab_end(gs_context *c, FrameCounters *ctr, cudaStream_t st);
+void launch_raster_slab(gs_context *c, const FrameParams *fp, FrameCounters *ctr, uint32_t n_tiles, const FrameBufs &b, bool depth,
+                        cudaStream_t st);
+void launch_resolve(gs_context *c, const FrameParams *fp, uint32_t n_tiles, cudaStream_t st);
 void launch_assemble(gs_context *c, const void *gathered, uint32_t tiles_per_rank, uint32_t world, uint32_t width,
                      uint32_t height, int32_t format, void *out_frame);
 

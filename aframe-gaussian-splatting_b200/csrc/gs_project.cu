@@ -34,16 +34,21 @@ __device__ __forceinline__ void unpack_int16(uint32_t value, float &lo, float &h
 // loads, 32 B + 4 B stores).  Splats rejected by the worker filter are skipped, except splat 0 which
 // the reference may draw through the zero tail of quirk Q5.
 // ---------------------------------------------------------------------------------------------
+// BY_ENTRY (slab path): one thread per ENTRY j of the current slab's draw order; record and rectangle are stored at j
+// (the slab's instances then carry j, not the splat index), and only the slab's splats are projected.
+template <bool BY_ENTRY>
 __global__ void __launch_bounds__(256) k_project(const float4 *__restrict__ cs, const uint4 *__restrict__ cc,
                                                  const float *__restrict__ depth,
                                                  const FrameParams *__restrict__ fp, float4 *__restrict__ rec_out,
-                                                 uint32_t *__restrict__ rect_out) {
+                                                 uint32_t *__restrict__ rect_out, const uint32_t *__restrict__ order,
+                                                 const FrameCounters *__restrict__ ctr) {
   const RenderConsts &rc = fp->rc;
-  const uint32_t n = fp->n_splats;
+  const uint32_t n = BY_ENTRY ? ctr->sort.n_valid : fp->n_splats;
   const uint32_t stride = gridDim.x * blockDim.x;
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+  for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) {
+    const uint32_t i = BY_ENTRY ? __ldg(order + j) : j;
     uint32_t rect = kNoRect;
-    const bool sorted = (__ldg(depth + i) != GS_DEPTH_REJECT) || (i == 0);
+    const bool sorted = BY_ENTRY || (__ldg(depth + i) != GS_DEPTH_REJECT) || (i == 0);
     if (sorted) {
       const float4 c = __ldg(cs + i);
       const float *mv = rc.mv, *P = rc.proj;
@@ -135,13 +140,13 @@ __global__ void __launch_bounds__(256) k_project(const float4 *__restrict__ cs, 
             rect = tx0 | (tx1 << 8) | (ty0 << 16) | (ty1 << 24);
             // rgba stay packed (converted to float(byte)/255.0, index.js:152-157, once per record in the raster);
             // the last slot carries gl_Position.z/w (index.js:163) for the depth test against foreign geometry
-            rec_out[2 * (size_t)i] = make_float4(cx, cy, a1x, a1y);
-            rec_out[2 * (size_t)i + 1] = make_float4(a2x, a2y, __uint_as_float(q.w), zndc);
+            rec_out[2 * (size_t)j] = make_float4(cx, cy, a1x, a1y);
+            rec_out[2 * (size_t)j + 1] = make_float4(a2x, a2y, __uint_as_float(q.w), zndc);
           }
         }
       }
     }
-    rect_out[i] = rect;
+    rect_out[j] = rect;
   }
 }
 
@@ -165,12 +170,16 @@ __device__ __forceinline__ uint32_t rect_count(uint32_t r, uint32_t rank, uint32
 // K3a: per draw-order entry: its splat, rectangle and exclusive instance offset inside its slice of 256
 // entries; per slice: its instance total; the LAST CTA to finish scans the slice totals (-> slice_prefix, D).
 // ---------------------------------------------------------------------------------------------
+// SLAB: rect is indexed by entry (k_project<true>), the entry's payload is j itself, and entries whose (small)
+// rectangle holds only closed bins own nothing any more.
+template <bool SLAB>
 __global__ void __launch_bounds__(kEmitThreads) k_count(const uint32_t *__restrict__ order,
                                                         const uint32_t *__restrict__ rect,
                                                         uint2 *__restrict__ ent, uint32_t *__restrict__ ent_off,
                                                         uint32_t *__restrict__ slice_total,
                                                         uint32_t *__restrict__ slice_prefix, FrameCounters *ctr,
-                                                        const FrameParams *__restrict__ fp) {
+                                                        const FrameParams *__restrict__ fp,
+                                                        const uint32_t *__restrict__ bin_open) {
   const uint32_t shard_rank = fp->rc.shard_rank, shard_world = fp->rc.shard_world;
   __shared__ uint32_t s_warp[kEmitThreads / 32], s_vis[kEmitThreads / 32];
   __shared__ uint32_t s_last;
@@ -181,10 +190,19 @@ __global__ void __launch_bounds__(kEmitThreads) k_count(const uint32_t *__restri
     const uint32_t j = sl * kEmitTile + tid;
     uint32_t idx = 0, r = kNoRect;
     if (j < nv) {
-      idx = __ldg(order + j);
+      idx = SLAB ? j : __ldg(order + j);
       r = __ldg(rect + idx);
     }
-    const uint32_t cnt = rect_count(r, shard_rank, shard_world);
+    uint32_t cnt = rect_count(r, shard_rank, shard_world);
+    if (SLAB && cnt) {
+      const uint32_t bx0 = r & 255u, bx1 = (r >> 8) & 255u, by0 = (r >> 16) & 255u, by1 = r >> 24;
+      if ((bx1 - bx0 + 1u) * (by1 - by0 + 1u) <= 4u) {  // bins of other ranks count as closed (k_slab_init)
+        bool any = false;
+        for (uint32_t by = by0; by <= by1; ++by)
+          for (uint32_t bx = bx0; bx <= bx1; ++bx) any = any || (__ldg(bin_open + by * fp->rc.bins_x + bx) != 0u);
+        if (!any) cnt = 0;
+      }
+    }
     uint32_t incl = cnt, vis = (r != kNoRect);
     for (int o = 1; o < 32; o <<= 1) {
       const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
@@ -283,7 +301,7 @@ __global__ void __launch_bounds__(kEmitThreads, 4) k_emit(const uint2 *__restric
                                                           const FrameParams *__restrict__ fp, uint64_t cap_inst,
                                                           uint16_t *__restrict__ inst_tile, uint32_t *__restrict__ inst_idx,
                                                           uint32_t *__restrict__ table_t1, uint32_t table_stride,
-                                                          FrameCounters *ctr) {
+                                                          FrameCounters *ctr, const uint32_t *__restrict__ bin_open) {
   const RenderConsts &rc = fp->rc;
   __shared__ uint32_t s_wi[kEmitThreads * (kEmitPerThread + 1)];  // stride 9: conflict-free staging
   __shared__ uint16_t s_wt[kEmitThreads * (kEmitPerThread + 1)];
@@ -439,6 +457,7 @@ __global__ void __launch_bounds__(kEmitThreads, 4) k_emit(const uint2 *__restric
             }
           }
           uint32_t t = kNoTile;
+          if (keep && bin_open) keep = __ldg(bin_open + ty * rc.bins_x + tx) != 0u;  // slab path: closed bins take nothing
           if (keep) {
             t = ty * rc.bins_x + tx;
             atomicAdd(&s_hist[t & 255u], 1u);
@@ -475,21 +494,41 @@ void launch_project(gs_context *c, const FrameParams *fp, const FrameBufs &b, cu
   const uint64_t cap = (uint64_t)c->sm_count * 16;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
-  k_project<<<(int)blocks, 256, 0, stream>>>(c->center_scale, c->cov_color, c->depth, fp, b.proj_rec, b.rect);
+  k_project<false><<<(int)blocks, 256, 0, stream>>>(c->center_scale, c->cov_color, c->depth, fp, b.proj_rec, b.rect, nullptr, nullptr);
 }
 
+void launch_project_entries(gs_context *c, const FrameParams *fp, FrameCounters *ctr, const FrameBufs &b, cudaStream_t stream) {
+  uint64_t blocks = ((uint64_t)c->cap + 255) / 256;
+  const uint64_t cap = (uint64_t)c->sm_count * 16;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  k_project<true><<<(int)blocks, 256, 0, stream>>>(c->center_scale, c->cov_color, c->depth, fp, b.proj_rec, b.rect, b.order, ctr);
+}
+
+static void launch_emit_impl(gs_context *c, const FrameParams *fp, FrameCounters *ctr, const FrameBufs &b, cudaStream_t st, bool slab);
 void launch_emit(gs_context *c, const FrameParams *fp, FrameCounters *ctr, const FrameBufs &b, cudaStream_t st) {
+  launch_emit_impl(c, fp, ctr, b, st, false);
+}
+void launch_emit_slab(gs_context *c, const FrameParams *fp, FrameCounters *ctr, const FrameBufs &b, cudaStream_t st) {
+  launch_emit_impl(c, fp, ctr, b, st, true);
+}
+static void launch_emit_impl(gs_context *c, const FrameParams *fp, FrameCounters *ctr, const FrameBufs &b, cudaStream_t st, bool slab) {
   uint64_t tiles = ((uint64_t)c->cap + kEmitTile - 1) / kEmitTile;
   const uint64_t cap = (uint64_t)c->sm_count * 8;
   if (tiles > cap) tiles = cap;
   if (tiles < 1) tiles = 1;
-  k_count<<<(int)tiles, kEmitThreads, 0, st>>>(b.order, b.rect, c->ent, c->ent_off, c->slice_total,
-                                                      c->slice_prefix, ctr, fp);
+  if (slab)
+    k_count<true><<<(int)tiles, kEmitThreads, 0, st>>>(b.order, b.rect, c->ent, c->ent_off, c->slice_total, c->slice_prefix, ctr, fp,
+                                                       c->bin_open);
+  else
+    k_count<false><<<(int)tiles, kEmitThreads, 0, st>>>(b.order, b.rect, c->ent, c->ent_off, c->slice_total, c->slice_prefix, ctr, fp,
+                                                        nullptr);
   uint64_t wins = (c->cap_inst + kEmitWindow - 1) / kEmitWindow;
   if (wins > (uint64_t)c->sm_count * 4) wins = (uint64_t)c->sm_count * 4;
   if (wins < 1) wins = 1;
   k_emit<<<(int)wins, kEmitThreads, 0, st>>>(c->ent, c->ent_off, c->slice_prefix, b.proj_rec, fp, c->cap_inst,
-                                                    c->inst_tile, c->inst_idx, c->table_d, c->table_d_stride, ctr);
+                                                    c->inst_tile, c->inst_idx, c->table_d, c->table_d_stride, ctr,
+                                                    slab ? c->bin_open : nullptr);
 }
 
 }  // namespace gs

@@ -128,13 +128,22 @@ struct RasterCfg {
   static constexpr int kMinBlocks = PACKED ? GS_RASTER_MINB : 4;
 };
 
+// slab path (gs_slab.cu): the pixel state lives in memory between the slabs of a frame
+struct SlabIO {
+  float4 *state;         // [tiles * 256] {R, G, B, T}, tile-major
+  uint8_t *closed;       // [tiles] every pixel of the tile is dead
+  uint32_t *bin_open;    // [bins] live tiles per bin
+  FrameCounters *ctr;    // open_bins
+};
+
 // DEPTH: depth-test every fragment LEQUAL against fp->depth_in (index.js:179-180).  STATS: count what the tile does
 // (and keep culling the whole list after the tile has closed, so that the count of 16x16 tile instances is exact).
-template <bool PACKED, bool DEPTH, bool STATS>
+// SLAB: one depth slab of a frame: start from / store back the pixel state, close saturated tiles; k_resolve writes the frame.
+template <bool PACKED, bool DEPTH, bool STATS, bool SLAB = false>
 __global__ void __launch_bounds__(RasterCfg<PACKED>::kThreads, RasterCfg<PACKED>::kMinBlocks) k_raster(const float4 *__restrict__ inst_rec,
                                                                         const uint2 *__restrict__ bin_range,
                                                                         const FrameParams *__restrict__ fp,
-                                                                        uint4 *__restrict__ tile_stats) {
+                                                                        uint4 *__restrict__ tile_stats, SlabIO slab) {
   using Cfg = RasterCfg<PACKED>;
   constexpr int kThreads = Cfg::kThreads, kChunk = Cfg::kChunk, kStages = Cfg::kStages, kCv = Cfg::kCv;
   constexpr int kWarps = kThreads / 32;
@@ -179,6 +188,7 @@ __global__ void __launch_bounds__(RasterCfg<PACKED>::kThreads, RasterCfg<PACKED>
   const uint32_t start = range.x, end = range.y;
   const uint32_t count = end - start;
   const uint32_t n_chunks = (count + kChunk - 1) / kChunk;
+  if (SLAB && (count == 0 || slab.closed[tile])) return;  // nothing of this slab reaches the tile / the tile is saturated
 
   if (tid == 0) {
     for (int s = 0; s < kStages; ++s) mbar_init(&s_full[s], 1);
@@ -205,6 +215,18 @@ __global__ void __launch_bounds__(RasterCfg<PACKED>::kThreads, RasterCfg<PACKED>
   float T0 = 1.0f, R0 = 0.0f, G0 = 0.0f, B0 = 0.0f;
   float2 T2 = make_float2(1.0f, 1.0f), R2 = make_float2(0.f, 0.f), G2 = R2, B2 = R2;
   float lim0 = inside0 ? 4.0f : -1.0f, lim1 = inside1 ? 4.0f : -1.0f;
+  if (SLAB) {  // continue where the nearer slabs left this tile
+    const float4 s0 = slab.state[(size_t)tile * 256 + ly * 16 + lx];
+    if (PACKED) {
+      const float4 s1 = slab.state[(size_t)tile * 256 + (ly + 1) * 16 + lx];
+      R2 = make_float2(s0.x, s1.x); G2 = make_float2(s0.y, s1.y); B2 = make_float2(s0.z, s1.z); T2 = make_float2(s0.w, s1.w);
+      lim0 = (inside0 && T2.x >= kTStop) ? 4.0f : -1.0f;
+      lim1 = (inside1 && T2.y >= kTStop) ? 4.0f : -1.0f;
+    } else {
+      R0 = s0.x; G0 = s0.y; B0 = s0.z; T0 = s0.w;
+      lim0 = (inside0 && T0 >= kTStop) ? 4.0f : -1.0f;
+    }
+  }
   const float2 fy2 = make_float2(fy, fy + 1.0f);
   uint32_t st_tests = 0, st_hits = 0, st_kept = 0;
   bool tile_alive = true;
@@ -332,7 +354,19 @@ __global__ void __launch_bounds__(RasterCfg<PACKED>::kThreads, RasterCfg<PACKED>
   }
   (void)tile_alive;
 
-  if (PACKED) {
+  if (SLAB) {
+    if (PACKED) {
+      slab.state[(size_t)tile * 256 + ly * 16 + lx] = make_float4(R2.x, G2.x, B2.x, T2.x);
+      slab.state[(size_t)tile * 256 + (ly + 1) * 16 + lx] = make_float4(R2.y, G2.y, B2.y, T2.y);
+    } else {
+      slab.state[(size_t)tile * 256 + ly * 16 + lx] = make_float4(R0, G0, B0, T0);
+    }
+    const int alive_end = __syncthreads_or((lim0 > 0.0f) || (lim1 > 0.0f));
+    if (!alive_end && tid == 0) {  // saturated: later slabs skip the tile, and the bin once all its tiles are closed
+      slab.closed[tile] = 1;
+      if (atomicSub(&slab.bin_open[bin], 1u) == 1u) atomicSub(&slab.ctr->open_bins, 1u);
+    }
+  } else if (PACKED) {
     store_pixel(fp, tile, tx, ty, lx, ly, x, y, inside0, T2.x, R2.x, G2.x, B2.x);
     store_pixel(fp, tile, tx, ty, lx, ly + 1, x, y + 1, inside1, T2.y, R2.y, G2.y, B2.y);
   } else {
@@ -411,7 +445,7 @@ void launch_raster(gs_context *c, const FrameParams *fp, uint32_t n_tiles, const
   uint4 *ts = c->tile_stats;
   switch (flags & 7u) {
 #define GS_RASTER_CASE(v, P, D, S) \
-  case v: k_raster<P, D, S><<<n_tiles, RasterCfg<P>::kThreads, 0, st>>>(b.inst_rec, b.bin_range, fp, ts); break;
+  case v: k_raster<P, D, S><<<n_tiles, RasterCfg<P>::kThreads, 0, st>>>(b.inst_rec, b.bin_range, fp, ts, SlabIO{}); break;
     GS_RASTER_CASE(0, false, false, false)
     GS_RASTER_CASE(1, true, false, false)
     GS_RASTER_CASE(2, false, true, false)
@@ -422,6 +456,32 @@ void launch_raster(gs_context *c, const FrameParams *fp, uint32_t n_tiles, const
     GS_RASTER_CASE(7, true, true, true)
 #undef GS_RASTER_CASE
   }
+}
+
+// one slab of a frame (always the packed pixel loop)
+void launch_raster_slab(gs_context *c, const FrameParams *fp, FrameCounters *ctr, uint32_t n_tiles, const FrameBufs &b, bool depth,
+                        cudaStream_t st) {
+  const SlabIO io{c->pix_state, c->tile_closed, c->bin_open, ctr};
+  if (depth)
+    k_raster<true, true, false, true><<<n_tiles, RasterCfg<true>::kThreads, 0, st>>>(b.inst_rec, b.bin_range, fp, nullptr, io);
+  else
+    k_raster<true, false, false, true><<<n_tiles, RasterCfg<true>::kThreads, 0, st>>>(b.inst_rec, b.bin_range, fp, nullptr, io);
+}
+
+// slab path epilogue: pixel state -> frame (composite over the clear colour; plain / tiled / peer destinations)
+__global__ void __launch_bounds__(256) k_resolve(const float4 *__restrict__ state, const FrameParams *__restrict__ fp) {
+  const RenderConsts &rc = fp->rc;
+  const uint32_t tile = blockIdx.x;
+  const uint32_t tx = tile % rc.tiles_x, ty = tile / rc.tiles_x;
+  if (rc.shard_world > 1 && ((tx / kTilesPerBin) % rc.shard_world) != rc.shard_rank) return;
+  const uint32_t lx = threadIdx.x & 15u, ly = threadIdx.x >> 4;
+  const uint32_t x = tx * kTile + lx, y = ty * kTile + ly;
+  const float4 s = state[(size_t)tile * 256 + threadIdx.x];
+  store_pixel(fp, tile, tx, ty, lx, ly, x, y, (x < rc.width) && (y < rc.height), s.w, s.x, s.y, s.z);
+}
+
+void launch_resolve(gs_context *c, const FrameParams *fp, uint32_t n_tiles, cudaStream_t st) {
+  k_resolve<<<n_tiles, 256, 0, st>>>(c->pix_state, fp);
 }
 
 void launch_peer_acquire(gs_context *c, const FrameParams *fp, FrameCounters *ctr, cudaStream_t st) {

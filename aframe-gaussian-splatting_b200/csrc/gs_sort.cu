@@ -13,36 +13,9 @@
 #include <type_traits>
 
 #include "gs_common.cuh"
+#include "gs_depthkey.cuh"
 
 namespace gs {
-
-// ECMAScript ToInt32 (index.js:561 `| 0`)
-__device__ __forceinline__ int32_t js_to_int32(double d) {
-  if (!isfinite(d)) return 0;
-  double t = trunc(d);
-  if (t >= -2147483648.0 && t <= 2147483647.0) return (int32_t)t;
-  double m = fmod(t, 4294967296.0);
-  if (m < 0) m += 4294967296.0;
-  return (int32_t)(uint32_t)m;
-}
-
-// index.js:561: sizeList[i] = ((depthList[i] - minDepth) * depthInv) | 0
-__device__ __forceinline__ int32_t depth_key(float depth_f32, double min_depth, double depth_inv) {
-  return js_to_int32(__dmul_rn(__dsub_rn((double)depth_f32, min_depth), depth_inv));
-}
-
-struct DepthRange {
-  double min_depth, depth_inv;
-};
-__device__ __forceinline__ DepthRange load_depth_range(const FrameCounters *ctr) {
-  // min is stored bit-inverted so that a zero-initialised word means "no value yet"
-  const double mn = dec_f64(~ctr->sort.min_enc);
-  const double mx = dec_f64(ctr->sort.max_enc);
-  DepthRange r;
-  r.min_depth = mn;
-  r.depth_inv = __ddiv_rn(65535.0, __dsub_rn(mx, mn));  // index.js:558
-  return r;
-}
 
 // ---------------------------------------------------------------------------------------------
 // K1: depth + cull + min/max (index.js:517-555).  Reads 16 B + 4 B per splat, writes 4 B.
@@ -124,7 +97,7 @@ __global__ void __launch_bounds__(256) k_depth_cull(const float4 *__restrict__ c
 // PASS_D1/D2: 16-bit depth key (index.js:557-567) low/high byte.  PASS_T1/T2: 16-bit tile id low/high byte;
 // T2's scatter gathers the 32 B projected record of each instance into its final per-tile slot.
 // ---------------------------------------------------------------------------------------------
-enum { PASS_D1 = 0, PASS_D2 = 1, PASS_T1 = 2, PASS_T2 = 3 };
+enum { PASS_D1 = 0, PASS_D2 = 1, PASS_T1 = 2, PASS_T2 = 3, PASS_S1 = 4 };  // S1: low key byte of a compacted slab (gs_slab.cu)
 
 struct RadixArgs {
   FrameCounters *ctr;
@@ -145,6 +118,9 @@ struct RadixArgs {
   uint32_t *inst_idx_b;
   const float4 *proj_rec;
   float4 *inst_rec;
+  // slab path: compacted (key, index) pairs of the current slab
+  const uint16_t *ckey;
+  const uint32_t *cidx;
 };
 
 template <int PASS>
@@ -152,6 +128,7 @@ __device__ __forceinline__ uint32_t pass_n(const RadixArgs &a) {
   const FrameCounters *ctr = a.ctr;
   if (PASS == PASS_D1) return ctr->sort.n_valid ? a.fp->n_splats : 0u;
   if (PASS == PASS_D2) return ctr->sort.n_inrange;
+  if (PASS == PASS_S1) return ctr->sort.n_valid;  // entries of the current slab (k_slab_begin)
   if (PASS == PASS_T1) return ctr->overflow ? 0u : (uint32_t)ctr->n_inst;
   return ctr->overflow ? 0u : ctr->n_inst_kept;
 }
@@ -170,6 +147,11 @@ __device__ __forceinline__ void load_elem(const RadixArgs &a, uint32_t i, const 
       if (key >= 0 && key <= 65535) { digit = key & 255; hi = (uint32_t)key >> 8; pay = i; }
       else ++dropped;  // typed-array write out of range: dropped (quirk Q5)
     }
+  } else if (PASS == PASS_S1) {
+    const uint32_t k = a.ckey[i];
+    digit = k & 255u;
+    hi = k >> 8;
+    pay = a.cidx[i];
   } else if (PASS == PASS_D2) {
     digit = a.dig_a[i];
     pay = a.idx_a[i];
@@ -285,7 +267,7 @@ __global__ void __launch_bounds__(kScatThreads, 2) k_radix_scatter(RadixArgs a) 
   __shared__ uint32_t s_pay[kRadixTile];
   // value carried to the next pass: D1 -> high key byte, T1/T2 -> the 16-bit tile id
   using hi_t = typename std::conditional<(PASS == PASS_T1 || PASS == PASS_T2), uint16_t, uint8_t>::type;
-  __shared__ hi_t s_hi[(PASS == PASS_D2) ? 1 : kRadixTile];
+  __shared__ hi_t s_hi[(PASS == PASS_D2) ? 1 : kRadixTile];  // D1 / S1: high key byte
   __shared__ uint8_t s_dig[kRadixTile];
   __shared__ uint32_t s_total;
   FrameCounters *ctr = a.ctr;
@@ -383,7 +365,7 @@ __global__ void __launch_bounds__(kScatThreads, 2) k_radix_scatter(RadixArgs a) 
     for (uint32_t i = tid; i < nvalid; i += kScatThreads) {
       const uint32_t pos = tile_off[s_dig[i]] + i;
       const uint32_t p = s_pay[i];
-      if (PASS == PASS_D1) {
+      if (PASS == PASS_D1 || PASS == PASS_S1) {
         a.idx_a[pos] = p;
         a.dig_a[pos] = s_hi[i];
       } else if (PASS == PASS_D2) {
@@ -474,6 +456,21 @@ void launch_tile_radix(gs_context *c, FrameCounters *ctr, const FrameBufs &b, cu
   a.stride = c->table_d_stride;
   run_pass<PASS_T1>(c, a, c->cap_inst, st);
   run_pass<PASS_T2>(c, a, c->cap_inst, st);
+}
+
+// slab path: stable sort of the compacted slab by its 16-bit key (6 launches) -> b.order = the slab's draw order
+void launch_slab_sort(gs_context *c, const FrameParams *fp, FrameCounters *ctr, const FrameBufs &b, cudaStream_t st) {
+  RadixArgs a = make_args(c, fp, ctr, b);
+  a.table = c->table_n;
+  a.totals = c->totals;
+  a.stride = c->table_n_stride;
+  a.ckey = c->ckey;
+  a.cidx = c->cidx;
+  const int grid = persistent_grid(c, c->cap, kRadixTile, 8);
+  k_radix_hist<PASS_S1><<<grid, kRadixThreads, 0, st>>>(a);
+  k_radix_scan<PASS_S1><<<256, 256, 0, st>>>(a);
+  k_radix_scatter<PASS_S1><<<grid, kScatThreads, 0, st>>>(a);
+  run_pass<PASS_D2>(c, a, c->cap, st);
 }
 
 void launch_tile_ranges(gs_context *c, FrameCounters *ctr, const FrameBufs &b, cudaStream_t st) {

@@ -225,3 +225,103 @@ def test_progressive_push_while_rendering(gs, orc):
             order = orc.sort(m[:k], fr.view)
             exp, _ = orc.render(cs[:k], cc[:k], order, fr.proj, fr.modelview, w, h, fr.focal)
             assert np.abs(out - exp).max() <= FRAME_TOL, k
+
+
+def _slab_ctx(gs, monkeypatch, slab_min, first):
+    monkeypatch.setenv("GS_SLAB_MIN", str(slab_min))
+    monkeypatch.setenv("GS_SLAB_FIRST", str(first))
+    return gs.SplatContext(0)
+
+
+@pytest.mark.parametrize("n,w,h,first", [(300000, 1000, 562, 20000), (60000, 640, 360, 3000), (500000, 1920, 1080, 50000)])
+def test_slab_path_equals_one_pass(gs, orc, ctx, monkeypatch, n, w, h, first):
+    """Front-to-back slab path (large scenes; forced here with GS_SLAB_MIN / GS_SLAB_FIRST): same frame as the one-pass
+    path BIT FOR BIT (a dead pixel ignores a splat whether or not it was binned), float / RGBA8 / depth-tested, and
+    within tolerance of the oracle."""
+    rows, cs, cc, m, fr = scene_inputs(gs, orc, n, 31337 + n, w, h)
+    order = orc.sort(m, fr.view)
+    depth = _depth_plane(orc, cs, cc, order, fr, w, h)
+    bg = (0.25, 0.5, 0.75, 0.5)
+    ctx.clear(); ctx.push_packed(cs, cc, m[:, 15])
+    ref32 = ctx.render(fr, bg=bg, fmt=gs.GS_FORMAT_RGBA32F).copy()
+    ref8 = ctx.render(fr, bg=bg, fmt=gs.GS_FORMAT_RGBA8).copy()
+    refd = ctx.render(fr, bg=bg, fmt=gs.GS_FORMAT_RGBA32F, depth_in=depth).copy()
+    st_ref = ctx.stats()
+    with _slab_ctx(gs, monkeypatch, 1000, first) as c:
+        c.push_packed(cs, cc, m[:, 15])
+        got32 = c.render(fr, bg=bg, fmt=gs.GS_FORMAT_RGBA32F)
+        st = c.stats()
+        assert np.array_equal(got32, ref32)
+        assert np.array_equal(c.render(fr, bg=bg, fmt=gs.GS_FORMAT_RGBA8), ref8)
+        assert np.array_equal(c.render(fr, bg=bg, fmt=gs.GS_FORMAT_RGBA32F, depth_in=depth), refd)
+        assert st["n_sorted"] == len(order) == st_ref["n_sorted"] and st["n_splats"] == n
+        assert st["kernel_launches"] > 40  # several slabs were scheduled
+        # pipelined: three slab frames in flight, different cameras
+        sc = gs.scenes
+        frames = [sc.make_frame(sc.orbit_camera(w, h, s), sc.demo_object(), w, h) for s in (0, 9, 33, 77)]
+        ctx.clear(); ctx.push_packed(cs, cc, m[:, 15])
+        exp = [ctx.render(f, fmt=gs.GS_FORMAT_RGBA8).copy() for f in frames]
+        outs = [c.pinned_array((h, w, 4), np.uint8) for _ in frames]
+        ts = [c.render_async(c.make_params(f, fmt=gs.GS_FORMAT_RGBA8), o.ctypes.data) for f, o in zip(frames[:3], outs[:3])]
+        c.wait(ts[0])
+        ts.append(c.render_async(c.make_params(frames[3], fmt=gs.GS_FORMAT_RGBA8), outs[3].ctypes.data))
+        for t in ts[1:]:
+            c.wait(t)
+        for o, e in zip(outs, exp):
+            assert np.array_equal(o, e)
+        # gs_sort and a stale-order draw still work on a slab-sized scene (they take the one-pass path)
+        assert np.array_equal(c.sort(fr.view), order)
+        stale = c.render(frames[1], fmt=gs.GS_FORMAT_RGBA8, reuse_sort=True)  # camera 1 drawn with fr's order
+        ctx.sort(fr.view, readback=False)
+        assert np.array_equal(stale, ctx.render(frames[1], fmt=gs.GS_FORMAT_RGBA8, reuse_sort=True))
+    exp32, _ = orc.render(cs, cc, order, fr.proj, fr.modelview, w, h, fr.focal, bg=bg)
+    assert np.abs(ref32 - exp32).max() <= FRAME_TOL
+
+
+def test_slab_path_quirk_q5_and_sharding(gs, orc, ctx, monkeypatch):
+    """Slab path corner cases: (1) quirk Q5 - dropped keys become repeats of splat 0 in front of everything; (2) the frame
+    sharded over emulated ranks (bin-column ownership) assembles to the unsharded frame."""
+    # (1) the Q5 scene of test_render_q5_tail_zero_draws_splat0
+    n = 4096
+    rng = np.random.default_rng(3)
+    cs = np.zeros((n, 4), np.float32)
+    cs[:, 0] = rng.uniform(-0.3, 0.3, n); cs[:, 1] = rng.uniform(-0.2, 0.2, n)
+    cs[:, 2] = (-1000.0 - np.arange(n, dtype=np.float64) * 1e-5).astype(np.float32)
+    cs[:, 3] = 30.0 / 32767.0
+    cc = np.zeros((n, 4), np.uint32)
+    q = lambda v: np.uint32(np.int16(v).view(np.uint16))
+    cc[:, 0] = q(20000); cc[:, 1] = q(32767) << 16; cc[:, 2] = q(32767) << 16
+    cc[:, 3] = rng.integers(0, 2 ** 32, n, dtype=np.uint64).astype(np.uint32) | np.uint32(0x60000000)
+    sa = np.ones(n, np.float32)
+    mm = np.zeros((n, 16), np.float32); mm[:, 12:15] = cs[:, :3]; mm[:, 15] = sa
+    W, H = 128, 96
+    P = np.zeros(16, np.float32); P[0] = 1.0; P[5] = -1.3; P[10] = -1.0; P[11] = -1.0; P[14] = -0.02
+    MV = np.eye(4, dtype=np.float32).reshape(16); MV[14] = 1e-4
+    view = np.array([MV[2], MV[6], MV[10], MV[14]], np.float32)
+    order = orc.sort(mm, view)
+    fr = gs.FrameInputs(proj=P, modelview=MV, view=view, width=W, height=H, focal=400.0)
+    exp, _ = orc.render(cs, cc, order, P, MV, W, H, 400.0)
+    with _slab_ctx(gs, monkeypatch, 100, 500) as c:
+        c.push_packed(cs, cc, sa)
+        got = c.render(fr, fmt=gs.GS_FORMAT_RGBA32F)
+        st = c.stats()
+        assert st["n_dropped"] > 0 and (order == 0).sum() >= 2 and st["n_sorted"] == len(order)
+        assert np.abs(got - exp).max() <= FRAME_TOL
+    # (2) sharded slab frames
+    rows, cs, cc, m, fr = scene_inputs(gs, orc, 120000, 2222, 1000, 562)
+    ctx.clear(); ctx.push_packed(cs, cc, m[:, 15])
+    ctx.set_shard(0, 1)
+    ref = ctx.render(fr, fmt=gs.GS_FORMAT_RGBA8, bg=(0.2, 0.1, 0.0, 0.3)).copy()
+    with _slab_ctx(gs, monkeypatch, 1000, 10000) as c:
+        c.push_packed(cs, cc, m[:, 15])
+        world = 3
+        sh = gs.dist.TileSharding(fr.width, fr.height, world)
+        tpr = sh.tiles_per_rank
+        tiles = []
+        for r in range(world):
+            c.set_shard(r, world)
+            p = c.make_params(fr, bg=(0.2, 0.1, 0.0, 0.3), fmt=gs.GS_FORMAT_RGBA8, flags=gs.GS_RENDER_OUT_TILED)
+            t = np.zeros((tpr, 256, 4), np.uint8)
+            c.render_raw(p, t.ctypes.data)
+            tiles.append(t)
+        assert np.array_equal(sh.assemble(np.stack(tiles)), ref)
