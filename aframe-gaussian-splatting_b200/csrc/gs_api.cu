@@ -147,15 +147,17 @@ static int ensure_tile_stats(gs_context *c, uint32_t n_tiles) {
 
 // buffers of the front-to-back slab path (gs_slab.cu); the pipeline is idle when this runs
 static int ensure_slab(gs_context *c, uint32_t n_tiles, uint32_t n_bins) {
-  if (c->slab_cap < c->cap || !c->key32) {
-    dev_free(c->key32); dev_free(c->cidx); dev_free(c->ckey); dev_free(c->chunk_cnt);
-    GS_CUDA(c, dev_alloc(&c->key32, (size_t)c->cap + 8));
+  if (c->slab_cap < c->cap || !c->key32[0]) {
+    dev_free(c->key32[0]); dev_free(c->key32[1]); dev_free(c->cidx); dev_free(c->ckey); dev_free(c->chunk_cnt);
+    GS_CUDA(c, dev_alloc(&c->key32[0], (size_t)c->cap + 8));
+    GS_CUDA(c, dev_alloc(&c->key32[1], (size_t)c->cap + 8));
     GS_CUDA(c, dev_alloc(&c->cidx, (size_t)c->cap));
     GS_CUDA(c, dev_alloc(&c->ckey, (size_t)c->cap));
     GS_CUDA(c, dev_alloc(&c->chunk_cnt, (size_t)c->cap / 2048 + 4));
     c->slab_cap = c->cap;
   }
-  if (!c->slab_tab) GS_CUDA(c, dev_alloc(&c->slab_tab, 1));
+  for (int i = 0; i < 2; ++i)
+    if (!c->slab_tab[i]) GS_CUDA(c, dev_alloc(&c->slab_tab[i], 1));
   if (c->slab_tiles_cap < n_tiles || !c->pix_state) {
     dev_free(c->pix_state); dev_free(c->tile_closed); dev_free(c->bin_open);
     GS_CUDA(c, dev_alloc(&c->pix_state, (size_t)n_tiles * 256));
@@ -180,6 +182,7 @@ static void drop_graphs(gs_context *c) {
   for (auto &sl : c->slot)
     for (int i = 0; i < 2; ++i) {
       kill(sl.graph_a[i][0]); kill(sl.graph_a[i][1]); kill(sl.graph_b[i]); kill(sl.graph_r[i]); kill(sl.graph_rp[i]);
+      kill(sl.graph_sa[i]); kill(sl.graph_sl[i][0]); kill(sl.graph_sl[i][1]);
     }
 }
 
@@ -259,7 +262,7 @@ extern "C" int gs_create(int device_ordinal, gs_context **out_ctx) {
   }
   if ((e = cudaMalloc((void **)&c->sort_hdr, sizeof(SortHeader))) != cudaSuccess) return bail("cudaMalloc", e);
   c->use_graphs = getenv("GS_NO_GRAPH") == nullptr;
-  // scenes of at least GS_SLAB_MIN resident splats (default 4 M) are rendered front to back in depth slabs (gs_slab.cu);
+  // frames expected to sort at least GS_SLAB_MIN splats (default 16 M) are rendered front to back in depth slabs (gs_slab.cu);
   // GS_SLAB_FIRST = target entry count of the nearest slab (default 1 M, the following ones double)
   if (const char *e = getenv("GS_SLAB_MIN")) c->slab_min = (uint32_t)strtoull(e, nullptr, 10);
   if (const char *e = getenv("GS_SLAB_FIRST")) c->slab_first = std::max<uint32_t>(1024u, (uint32_t)strtoull(e, nullptr, 10));
@@ -312,7 +315,8 @@ extern "C" int gs_destroy(gs_context *c) {
   if (c->peer_local) cudaFree(c->peer_local);
   dev_free(c->table_n); dev_free(c->table_d); dev_free(c->slice_total); dev_free(c->totals); dev_free(c->sort_hdr);
   dev_free(c->slice_prefix); dev_free(c->ent); dev_free(c->ent_off);
-  dev_free(c->key32); dev_free(c->cidx); dev_free(c->ckey); dev_free(c->chunk_cnt); dev_free(c->slab_tab);
+  dev_free(c->key32[0]); dev_free(c->key32[1]); dev_free(c->cidx); dev_free(c->ckey); dev_free(c->chunk_cnt);
+  dev_free(c->slab_tab[0]); dev_free(c->slab_tab[1]);
   dev_free(c->pix_state); dev_free(c->tile_closed); dev_free(c->bin_open);
   for (auto &sl : c->slot) {
     dev_free(sl.ctr); dev_free(sl.fp);
@@ -356,6 +360,7 @@ extern "C" int gs_clear(gs_context *c) {
   GS_CUDA(c, cudaStreamSynchronize(c->push_stream));
   c->n = 0;
   c->have_order = false;
+  c->have_last_sorted = false;
   c->order_count = 0;
   return GS_OK;
 }
@@ -661,53 +666,98 @@ static int launch_frame(gs_context *c, gs_context::Slot &sl, bool reuse, uint32_
   return GS_OK;
 }
 
-// Front-to-back slab path (gs_slab.cu): the whole frame is one chain on the raster stream - its kernels are large (the
-// path is for scenes of millions of splats) and every slab depends on the tiles the previous one closed.
-static int launch_frame_slabs(gs_context *c, gs_context::Slot &sl, uint32_t n_tiles, uint32_t n_bins) {
+// entries covered by the first k slabs: slab_first * (1 + 4 + 16 + ...) - each slab is 4x the previous one
+static uint64_t slab_cumulative(uint32_t first, int k) { return (uint64_t)first * (((1ull << (2 * k)) - 1ull) / 3ull); }
+
+// Stage A of a slab frame (sort stream): depth + cull, keys + bucket histogram, slab plan, pixel-state reset.
+static cudaError_t enqueue_slab_keys_stage(gs_context *c, gs_context::Slot &sl, bool external_events) {
+  auto rec = [&](cudaEvent_t ev, cudaStream_t st) {
+    return external_events ? cudaEventRecordWithFlags(ev, st, cudaEventRecordExternal) : cudaEventRecord(ev, st);
+  };
+  cudaStream_t st = c->stream;
+  cudaError_t e;
+  if ((e = cudaMemcpyAsync(sl.fp, sl.fp_host, sizeof(FrameParams), cudaMemcpyHostToDevice, st))) return e;
+  if ((e = cudaMemsetAsync(sl.ctr, 0, sizeof(FrameCounters), st))) return e;
+  if ((e = rec(sl.ev[0], st))) return e;
+  launch_depth_cull(c, sl.fp, sl.ctr, st);
+  launch_keys(c, sl.fp, sl.ctr, sl.set, st);
+  launch_slab_plan(c, sl.fp, sl.ctr, sl.set, c->slab_first, sl.n_slabs, st);
+  if ((e = rec(sl.ev[1], st))) return e;
+  return cudaGetLastError();
+}
+
+// Stage B+C of a slab frame (raster stream): the slab loop and the resolve.  One chain: every slab depends on the tiles
+// the previous one closed.
+static cudaError_t enqueue_slab_loop_stage(gs_context *c, gs_context::Slot &sl, uint32_t n_tiles, uint32_t n_bins,
+                                           bool external_events) {
+  auto rec = [&](cudaEvent_t ev, cudaStream_t st) {
+    return external_events ? cudaEventRecordWithFlags(ev, st, cudaEventRecordExternal) : cudaEventRecord(ev, st);
+  };
   cudaStream_t st = c->rstream;
   const FrameBufs b = slot_bufs(c, sl);
-  const int set = sl.set;
-  if (c->sort_set_free[set]) GS_CUDA(c, cudaStreamWaitEvent(st, c->sort_set_free[set], 0));
-  if (c->bin_set_free[set]) GS_CUDA(c, cudaStreamWaitEvent(st, c->bin_set_free[set], 0));
-  if (c->pushed) GS_CUDA(c, cudaStreamWaitEvent(st, c->push_done, 0));
-  GS_CUDA(c, cudaMemcpyAsync(sl.fp, sl.fp_host, sizeof(FrameParams), cudaMemcpyHostToDevice, st));
-  GS_CUDA(c, cudaMemsetAsync(sl.ctr, 0, sizeof(FrameCounters), st));
-  GS_CUDA(c, cudaEventRecord(sl.ev[0], st));
-  launch_depth_cull(c, sl.fp, sl.ctr, st);
-  launch_keys(c, sl.fp, sl.ctr, st);
-  // slabs of slab_first, 2x, 4x ... entries: enough of them to cover every resident splat
-  int n_slabs = 1;
-  while (n_slabs < kMaxSlabs && (uint64_t)c->slab_first * ((1ull << n_slabs) - 1ull) < sl.n_splats) ++n_slabs;
-  sl.n_slabs = n_slabs;
-  launch_slab_plan(c, sl.fp, sl.ctr, c->slab_first, n_slabs, st);
-  GS_CUDA(c, cudaEventRecord(sl.ev[1], st));
-  GS_CUDA(c, cudaEventRecord(sl.ev[2], st));
-  for (int s = 0; s < n_slabs; ++s) {
-    launch_slab_begin(c, sl.fp, sl.ctr, s, st);           // entry count (0 once every bin is closed) + compaction
+  cudaError_t e;
+  launch_slab_init(c, sl.fp, sl.ctr, st);
+  if ((e = rec(sl.ev[2], st))) return e;
+  for (int s = 0; s < sl.n_slabs; ++s) {
+    launch_slab_begin(c, sl.fp, sl.ctr, sl.set, s, st);   // entry count (0 once every bin is closed) + compaction
     launch_slab_sort(c, sl.fp, sl.ctr, b, st);            // draw order of the slab
     launch_project_entries(c, sl.fp, sl.ctr, b, st);      // vertex shader for the slab's entries
-    GS_CUDA(c, cudaMemsetAsync(b.bin_range, 0, sizeof(uint2) * (size_t)n_bins, st));
+    if ((e = cudaMemsetAsync(b.bin_range, 0, sizeof(uint2) * (size_t)n_bins, st))) return e;
     launch_emit_slab(c, sl.fp, sl.ctr, b, st);
     launch_tile_radix(c, sl.ctr, b, st);
     launch_tile_ranges(c, sl.ctr, b, st);
-    for (int k = 0; k < 2; ++k)
-      if (!sl.slab_ev[s][k]) GS_CUDA(c, cudaEventCreate(&sl.slab_ev[s][k]));
-    GS_CUDA(c, cudaEventRecord(sl.slab_ev[s][0], st));
+    if ((e = rec(sl.slab_ev[s][0], st))) return e;
     launch_raster_slab(c, sl.fp, sl.ctr, n_tiles, b, (sl.raster_flags & 2u) != 0, st);
-    GS_CUDA(c, cudaEventRecord(sl.slab_ev[s][1], st));
+    if ((e = rec(sl.slab_ev[s][1], st))) return e;
   }
   launch_slab_end(c, sl.ctr, st);
-  GS_CUDA(c, cudaEventRecord(sl.ev[3], st));
+  if ((e = rec(sl.ev[3], st))) return e;
   if (sl.peer) launch_peer_acquire(c, sl.fp, sl.ctr, st);
-  GS_CUDA(c, cudaEventRecord(sl.ev_r0, st));
+  if ((e = rec(sl.ev_r0, st))) return e;
   launch_resolve(c, sl.fp, n_tiles, st);
-  GS_CUDA(c, cudaEventRecord(sl.ev[4], st));
+  if ((e = rec(sl.ev[4], st))) return e;
   if (sl.peer) launch_peer_signal_wait(c, sl.fp, sl.ctr, st);
-  GS_CUDA(c, cudaGetLastError());
-  GS_CUDA(c, cudaEventRecord(sl.ev_sorted, st));
-  GS_CUDA(c, cudaEventRecord(sl.ev_binned, st));
+  return cudaGetLastError();
+}
+
+// Front-to-back slab path (gs_slab.cu).  Two stages: A (keys of every splat, O(N), sort stream) and the slab loop
+// (raster stream); stage A of frame k+1 runs under the loop of frame k (keys / slab table are double-buffered by set).
+static int launch_frame_slabs(gs_context *c, gs_context::Slot &sl, uint32_t n_tiles, uint32_t n_bins) {
+  gs_context::GraphKey k;
+  k.cap = c->cap; k.n_tiles = n_tiles; k.cap_inst = c->cap_inst; k.p0 = c->depth; k.p1 = c->inst_rec[0]; k.p2 = c->center_scale;
+  if (memcmp(&k, &c->gkey, sizeof(k)) != 0) {
+    drop_graphs(c);
+    c->gkey = k;
+  }
+  const int set = sl.set;
+  // slabs of slab_first, 4x, 16x ... entries: enough of them to cover every resident splat
+  int n_slabs = 1;
+  while (n_slabs < kMaxSlabs && slab_cumulative(c->slab_first, n_slabs) < sl.n_splats) ++n_slabs;
+  if (n_slabs != sl.graph_slabs[set]) {  // the captured loop bakes the slab count
+    auto kill = [](cudaGraphExec_t &g) { if (g) { cudaGraphExecDestroy(g); g = nullptr; } };
+    kill(sl.graph_sa[set]); kill(sl.graph_sl[set][0]); kill(sl.graph_sl[set][1]);
+    sl.graph_slabs[set] = n_slabs;
+  }
+  sl.n_slabs = n_slabs;
+  for (int s = 0; s < n_slabs; ++s)
+    for (int q = 0; q < 2; ++q)
+      if (!sl.slab_ev[s][q]) GS_CUDA(c, cudaEventCreate(&sl.slab_ev[s][q]));
+  // A: the keys / slab table of this set must no longer be read by the loop that used them last
+  if (c->sort_set_free[set]) GS_CUDA(c, cudaStreamWaitEvent(c->stream, c->sort_set_free[set], 0));
+  int rc = run_graph(c, sl.graph_sa[set], c->stream, [&](bool ext) { return enqueue_slab_keys_stage(c, sl, ext); });
+  if (rc) return rc;
+  GS_CUDA(c, cudaEventRecord(sl.ev_sorted, c->stream));
+  // loop: needs A of this frame; consecutive loops are ordered by the stream itself
+  GS_CUDA(c, cudaStreamWaitEvent(c->rstream, sl.ev_sorted, 0));
+  if (sl.peer) {
+    GS_CUDA(c, enqueue_slab_loop_stage(c, sl, n_tiles, n_bins, false));
+  } else if ((rc = run_graph(c, sl.graph_sl[set][(sl.raster_flags & 2u) ? 1 : 0], c->rstream,
+                             [&](bool ext) { return enqueue_slab_loop_stage(c, sl, n_tiles, n_bins, ext); }))) {
+    return rc;
+  }
+  GS_CUDA(c, cudaEventRecord(sl.ev_binned, c->rstream));
   c->sort_set_free[set] = sl.ev_binned;
-  sl.launches = 4u + (uint32_t)n_slabs * 21u + 2u;
+  sl.launches = 4u + 1u + (uint32_t)n_slabs * 21u + 2u;
   return GS_OK;
 }
 
@@ -911,6 +961,8 @@ static int wait_slot(gs_context *c, gs_context::Slot &sl, gs_stats *stats) {
   }
   cudaEventElapsedTime(&c->stats.ms_total, sl.ev[0], sl.ev[4]);
   c->order_count = sl.ctr_host->sort.n_valid;
+  c->last_sorted = sl.ctr_host->sort.n_valid;
+  c->have_last_sorted = true;
   if (stats) *stats = c->stats;
   return GS_OK;
 }
@@ -931,7 +983,9 @@ extern "C" int gs_render_async(gs_context *c, const gs_render_params *p, void *o
   if ((p->flags & GS_RENDER_REUSE_SORT) && c->have_order && (rcode = drain(c))) return rcode;  // runs in the last sort's buffers
   if ((p->flags & GS_RENDER_STATS) && (rcode = drain(c))) return rcode;  // the per-tile statistics buffer is not double-buffered
   // large scenes render front to back in depth slabs; the two paths share scratch buffers, so a change drains
-  const bool slab = c->n >= c->slab_min && !(p->flags & (GS_RENDER_REUSE_SORT | GS_RENDER_STATS));
+  // (the criterion is the number of SORTED splats: the last frame's count when there is one, else the resident count)
+  const uint32_t expect_sorted = c->have_last_sorted ? c->last_sorted : c->n;
+  const bool slab = expect_sorted >= c->slab_min && !(p->flags & (GS_RENDER_REUSE_SORT | GS_RENDER_STATS));
   if ((int)slab != c->last_mode) {
     if ((rcode = drain(c))) return rcode;
     GS_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -940,7 +994,7 @@ extern "C" int gs_render_async(gs_context *c, const gs_render_params *p, void *o
     c->last_mode = (int)slab;
   }
   // growing any shared buffer needs an idle pipeline
-  const bool grow = (slab && (c->slab_cap < c->cap || !c->key32 || c->slab_tiles_cap < n_tiles || !c->slab_tab)) || !(c->scratch_cap >= c->cap && c->depth) || !(n_bins <= c->bins_cap && c->bin_range[0]) || !(n_tiles <= c->tile_stats_cap && c->tile_stats) || c->cap_inst == 0;
+  const bool grow = (slab && (c->slab_cap < c->cap || !c->key32[0] || c->slab_tiles_cap < n_tiles || !c->slab_tab[1])) || !(c->scratch_cap >= c->cap && c->depth) || !(n_bins <= c->bins_cap && c->bin_range[0]) || !(n_tiles <= c->tile_stats_cap && c->tile_stats) || c->cap_inst == 0;
   if (grow) {
     if ((rcode = drain(c))) return rcode;
     GS_CUDA(c, cudaStreamSynchronize(c->stream));

@@ -111,7 +111,7 @@ struct FrameParams {
 
 
 // ---- front-to-back slab path ----
-constexpr int kMaxSlabs = 12;          // geometric slab sizes: 1 M, 2 M, 4 M ... entries (nearest first)
+constexpr int kMaxSlabs = 8;           // geometric slab sizes: 1 M, 4 M, 16 M ... entries (nearest first)
 constexpr int kSlabBuckets = 4096;     // slab boundaries are chosen on a 4096-bucket histogram of the 16-bit keys
 constexpr uint32_t kNoKey = 0xFFFFFFFFu;
 struct SlabTable {
@@ -170,16 +170,18 @@ struct gs_context {
   uint2 *bin_range[2] = {nullptr, nullptr};  // [bins] {start, end} into inst_rec, one per slot (read by the raster)
   // ---- front-to-back slab path (gs_slab.cu): allocated when a scene first crosses the slab threshold ----
   uint32_t slab_cap = 0;           // splats the per-splat slab buffers are sized for
-  uint32_t *key32 = nullptr;       // [cap] 16-bit depth key of every splat, kNoKey if not in the sort
+  uint32_t *key32[2] = {nullptr, nullptr};  // [cap] 16-bit depth key of every splat, kNoKey if not in the sort (one per set)
   uint32_t *cidx = nullptr;        // [cap] splat indices of the current slab, in index order
   uint16_t *ckey = nullptr;        // [cap] their keys
   uint32_t *chunk_cnt = nullptr;   // [cap / 2048 + 2] compaction offsets
-  gs::SlabTable *slab_tab = nullptr;
+  gs::SlabTable *slab_tab[2] = {nullptr, nullptr};
   float4 *pix_state = nullptr;     // [tiles * 256] {R, G, B, T} carried from slab to slab
   uint8_t *tile_closed = nullptr;  // [tiles]
   uint32_t *bin_open = nullptr;    // [bins] live tiles per bin (0 for bins of other ranks)
   uint32_t slab_tiles_cap = 0;
-  uint32_t slab_min = 4u << 20;    // scenes with at least this many resident splats render front to back in slabs
+  uint32_t slab_min = 16u << 20;   // frames expected to SORT at least this many splats render front to back in slabs
+  uint32_t last_sorted = 0;        // V of the most recently completed frame (predicts the next frame's)
+  bool have_last_sorted = false;
   uint32_t slab_first = 1u << 20;  // target entry count of the nearest slab (the following ones double)
   int last_mode = 0;               // 0 = one pass (three-stage pipeline), 1 = slab path
   uint4 *tile_stats = nullptr;     // [tiles] per-tile counts of a GS_RENDER_STATS frame
@@ -212,6 +214,9 @@ struct gs_context {
     cudaGraphExec_t graph_b[2] = {nullptr, nullptr};                           // binning, [set]
     cudaGraphExec_t graph_r[2] = {nullptr, nullptr};                           // raster, [set]
     cudaGraphExec_t graph_rp[2] = {nullptr, nullptr};                          // acquire + raster + signal/wait (fused exchange)
+    cudaGraphExec_t graph_sa[2] = {nullptr, nullptr};                          // slab path: keys stage, [set]
+    cudaGraphExec_t graph_sl[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};  // slab path: slab loop + resolve, [set][depth]
+    int graph_slabs[2] = {0, 0};                                               // slab count baked into graph_sl
     bool peer = false;
     uint64_t ticket = 0;
     int ring = 0;                            // slot of the shared frame ring (fused exchange)
@@ -299,9 +304,10 @@ struct PeerRows { unsigned long long *p[kMaxPeers]; };
 void launch_peer_release(gs_context *c, const PeerRows &rows, uint32_t world, uint32_t rank, unsigned long long seq,
                          cudaStream_t st);
 // ---- slab path launchers (gs_slab.cu / gs_raster.cu) ----
-void launch_keys(gs_context *c, const FrameParams *fp, FrameCounters *ctr, cudaStream_t st);          // keys + bucket histogram
-void launch_slab_plan(gs_context *c, const FrameParams *fp, FrameCounters *ctr, uint32_t first_target, int n_slabs, cudaStream_t st);
-void launch_slab_begin(gs_context *c, const FrameParams *fp, FrameCounters *ctr, int slab, cudaStream_t st);  // + compaction: 4 launches
+void launch_keys(gs_context *c, const FrameParams *fp, FrameCounters *ctr, int set, cudaStream_t st);  // keys + bucket histogram
+void launch_slab_plan(gs_context *c, const FrameParams *fp, FrameCounters *ctr, int set, uint32_t first_target, int n_slabs, cudaStream_t st);
+void launch_slab_init(gs_context *c, const FrameParams *fp, FrameCounters *ctr, cudaStream_t st);
+void launch_slab_begin(gs_context *c, const FrameParams *fp, FrameCounters *ctr, int set, int slab, cudaStream_t st);  // + compaction: 4 launches
 void launch_slab_sort(gs_context *c, const FrameParams *fp, FrameCounters *ctr, const FrameBufs &b, cudaStream_t st);  // 6 launches
 void launch_project_entries(gs_context *c, const FrameParams *fp, FrameCounters *ctr, const FrameBufs &b, cudaStream_t st);
 void launch_emit_slab(gs_context *c, const FrameParams *fp, FrameCounters *ctr, const FrameBufs &b, cudaStream_t st);

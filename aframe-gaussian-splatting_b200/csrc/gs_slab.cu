@@ -8,7 +8,7 @@
 // part of the scene that is seen:
 //
 //   once per frame   k_keys        the reference's 16-bit key of every sorted splat (index.js:561) + a 4096-bucket histogram
-//                    k_slab_plan   slab boundaries on the key axis, nearest first: ~1 M, 2 M, 4 M ... entries
+//                    k_slab_plan   slab boundaries on the key axis, nearest first: ~1 M, 4 M, 16 M ... entries
 //                    k_slab_init   per-pixel state {R, G, B, T}, per-tile closed flags, per-bin live-tile counts
 //   per slab         k_slab_begin  entry count of the slab; 0 when no bin is open any more (every later kernel then
 //                                  finds nothing to do)
@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(256) k_keys(const float *__restrict__ depth, c
 
 // ---------------------------------------------------------------------------------------------
 // slab boundaries: one CTA of 1024 threads.  S[b] = entries with bucket >= b (suffix sums); slab s ends at the
-// highest bucket b with S[b] >= first_target * (2^(s+1) - 1), the last non-empty slab takes the rest.
+// highest bucket b with S[b] >= first_target * (1 + 4 + ... + 4^s), the last scheduled slab takes the rest.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024) k_slab_plan(SlabTable *tab, FrameCounters *ctr, uint32_t first_target, int n_slabs) {
   __shared__ uint32_t S[kSlabBuckets + 1];
@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(1024) k_slab_plan(SlabTable *tab, FrameCounter
     // boundary bucket of slab tid-1 (s_bound[0] = 4096: nothing taken yet)
     uint32_t b = kSlabBuckets;
     if (tid > 0) {
-      const unsigned long long target = (unsigned long long)first_target * ((1ull << tid) - 1ull);
+      const unsigned long long target = (unsigned long long)first_target * (((1ull << (2 * tid)) - 1ull) / 3ull);  // 1 + 4 + 16 ...
       if (tid >= (uint32_t)n_slabs || target >= total) {
         b = 0;  // the rest
       } else {
@@ -314,23 +314,28 @@ static int grid_for(gs_context *c, uint64_t n, int per_cta, int per_sm) {
   return (int)(t < cap ? t : cap);
 }
 
-void launch_keys(gs_context *c, const FrameParams *fp, FrameCounters *ctr, cudaStream_t st) {
-  cudaMemsetAsync(c->slab_tab, 0, sizeof(SlabTable), st);
-  k_keys<<<grid_for(c, c->cap, 256 * 8, 4), 256, 0, st>>>(c->depth, fp, ctr, c->key32, c->slab_tab);
+void launch_keys(gs_context *c, const FrameParams *fp, FrameCounters *ctr, int set, cudaStream_t st) {
+  cudaMemsetAsync(c->slab_tab[set], 0, sizeof(SlabTable), st);
+  k_keys<<<grid_for(c, c->cap, 256 * 8, 4), 256, 0, st>>>(c->depth, fp, ctr, c->key32[set], c->slab_tab[set]);
 }
 
-void launch_slab_plan(gs_context *c, const FrameParams *fp, FrameCounters *ctr, uint32_t first_target, int n_slabs, cudaStream_t st) {
-  k_slab_plan<<<1, 1024, 0, st>>>(c->slab_tab, ctr, first_target, n_slabs);
+void launch_slab_plan(gs_context *c, const FrameParams *fp, FrameCounters *ctr, int set, uint32_t first_target, int n_slabs,
+                      cudaStream_t st) {
+  k_slab_plan<<<1, 1024, 0, st>>>(c->slab_tab[set], ctr, first_target, n_slabs);
+}
+
+// pixel state / closed flags are shared by all frames: reset at the start of a frame's slab loop (raster stream)
+void launch_slab_init(gs_context *c, const FrameParams *fp, FrameCounters *ctr, cudaStream_t st) {
   k_slab_init<<<grid_for(c, (uint64_t)c->slab_tiles_cap * 256, 256 * 4, 8), 256, 0, st>>>(fp, ctr, c->pix_state, c->tile_closed,
                                                                                            c->bin_open);
 }
 
-void launch_slab_begin(gs_context *c, const FrameParams *fp, FrameCounters *ctr, int slab, cudaStream_t st) {
-  k_slab_begin<<<1, 32, 0, st>>>(c->slab_tab, ctr, slab);
+void launch_slab_begin(gs_context *c, const FrameParams *fp, FrameCounters *ctr, int set, int slab, cudaStream_t st) {
+  k_slab_begin<<<1, 32, 0, st>>>(c->slab_tab[set], ctr, slab);
   const int grid = grid_for(c, c->cap, kCompactChunk, 8);
-  k_compact_count<<<grid, kCompactThreads, 0, st>>>(c->key32, fp, ctr, c->slab_tab, slab, c->chunk_cnt);
+  k_compact_count<<<grid, kCompactThreads, 0, st>>>(c->key32[set], fp, ctr, c->slab_tab[set], slab, c->chunk_cnt);
   k_compact_scan<<<1, 1024, 0, st>>>(c->chunk_cnt, fp, ctr);
-  k_compact_write<<<grid, kCompactThreads, 0, st>>>(c->key32, fp, ctr, c->slab_tab, slab, c->chunk_cnt, c->cidx, c->ckey);
+  k_compact_write<<<grid, kCompactThreads, 0, st>>>(c->key32[set], fp, ctr, c->slab_tab[set], slab, c->chunk_cnt, c->cidx, c->ckey);
 }
 
 void launch_slab_end(gs_context *c, FrameCounters *ctr, cudaStream_t st) { k_slab_end<<<1, 32, 0, st>>>(ctr); }
