@@ -9,6 +9,7 @@ class Splats : public Napi::ObjectWrap<Splats> {
   static Napi::Object Init(Napi::Env env, Napi::Object exports) {
     exports.Set("Splats", DefineClass(env, "Splats", {
       InstanceMethod("clear", &Splats::Clear), InstanceMethod("push", &Splats::Push),
+      InstanceMethod("reserve", &Splats::Reserve),
       InstanceMethod("sort", &Splats::Sort),   InstanceMethod("render", &Splats::Render)}));
     return exports;
   }
@@ -20,6 +21,11 @@ class Splats : public Napi::ObjectWrap<Splats> {
  private:
   void Check(Napi::Env e, int rc) { if (rc != GS_OK) Napi::Error::New(e, gs_last_error(ctx_)).ThrowAsJavaScriptException(); }
   Napi::Value Clear(const Napi::CallbackInfo& i) { Check(i.Env(), gs_clear(ctx_)); return i.Env().Undefined(); }
+  // reserve(numVertexes)                           <- initGL(numVertexes), index.js:248-251
+  Napi::Value Reserve(const Napi::CallbackInfo& i) {
+    Check(i.Env(), gs_reserve(ctx_, i[0].As<Napi::Number>().Uint32Value()));
+    return i.Env().Undefined();
+  }
   // push(ArrayBuffer rows, vertexCount)            <- pushDataBuffer(buffer, vertexCount), index.js:328
   Napi::Value Push(const Napi::CallbackInfo& i) {
     auto buf = i[0].As<Napi::ArrayBuffer>();
@@ -35,7 +41,7 @@ class Splats : public Napi::ObjectWrap<Splats> {
     Check(i.Env(), gs_sort(ctx_, view.Data(), cut, out.Data(), &cnt));
     return Napi::Uint32Array::New(i.Env(), cnt, out.ArrayBuffer(), 0);
   }
-  // render({proj, modelview, width, height, focal, cutout?, bg?}, Uint8Array out)  <- onBeforeRender + draw
+  // render({proj, modelview, width, height, focal, cutout?, bg?, depth?: Float32Array}, Uint8Array out)  <- onBeforeRender + draw
   Napi::Value Render(const Napi::CallbackInfo& i) {
     auto o = i[0].As<Napi::Object>();
     gs_render_params p{};
@@ -45,6 +51,7 @@ class Splats : public Napi::ObjectWrap<Splats> {
     p.height = o.Get("height").As<Napi::Number>().Uint32Value();
     p.focal = o.Get("focal").As<Napi::Number>().FloatValue();
     if (o.Has("cutout")) { p.has_cutout = 1; memcpy(p.cutout16, o.Get("cutout").As<Napi::Float32Array>().Data(), 64); }
+    if (o.Has("depth")) p.depth_in = o.Get("depth").As<Napi::Float32Array>().Data();  // gl.readPixels(DEPTH) of the scene so far
     p.out_format = GS_FORMAT_RGBA8;
     Check(i.Env(), gs_render(ctx_, &p, i[1].As<Napi::Uint8Array>().Data(), nullptr));
     return i.Env().Undefined();
