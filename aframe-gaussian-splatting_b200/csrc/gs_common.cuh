@@ -111,7 +111,7 @@ struct FrameParams {
 
 
 // ---- front-to-back slab path ----
-constexpr int kMaxSlabs = 8;           // geometric slab sizes: 1 M, 4 M, 16 M ... entries (nearest first)
+constexpr int kMaxSlabs = 12;          // geometric slab sizes: 1 M, 2 M, 4 M ... entries (nearest first)
 constexpr int kSlabBuckets = 4096;     // slab boundaries are chosen on a 4096-bucket histogram of the 16-bit keys
 constexpr uint32_t kNoKey = 0xFFFFFFFFu;
 struct SlabTable {

@@ -8,7 +8,7 @@
 // part of the scene that is seen:
 //
 //   once per frame   k_keys        the reference's 16-bit key of every sorted splat (index.js:561) + a 4096-bucket histogram
-//                    k_slab_plan   slab boundaries on the key axis, nearest first: ~1 M, 4 M, 16 M ... entries
+//                    k_slab_plan   slab boundaries on the key axis, nearest first: ~1 M, 2 M, 4 M ... entries
 //                    k_slab_init   per-pixel state {R, G, B, T}, per-tile closed flags, per-bin live-tile counts
 //   per slab         k_slab_begin  entry count of the slab; 0 when no bin is open any more (every later kernel then
 //                                  finds nothing to do)
@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(256) k_keys(const float *__restrict__ depth, c
 
 // ---------------------------------------------------------------------------------------------
 // slab boundaries: one CTA of 1024 threads.  S[b] = entries with bucket >= b (suffix sums); slab s ends at the
-// highest bucket b with S[b] >= first_target * (1 + 4 + ... + 4^s), the last scheduled slab takes the rest.
+// highest bucket b with S[b] >= first_target * (2^(s+1) - 1), the last scheduled slab takes the rest.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024) k_slab_plan(SlabTable *tab, FrameCounters *ctr, uint32_t first_target, int n_slabs) {
   __shared__ uint32_t S[kSlabBuckets + 1];
@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(1024) k_slab_plan(SlabTable *tab, FrameCounter
     // boundary bucket of slab tid-1 (s_bound[0] = 4096: nothing taken yet)
     uint32_t b = kSlabBuckets;
     if (tid > 0) {
-      const unsigned long long target = (unsigned long long)first_target * (((1ull << (2 * tid)) - 1ull) / 3ull);  // 1 + 4 + 16 ...
+      const unsigned long long target = (unsigned long long)first_target * ((1ull << tid) - 1ull);  // 1 + 2 + 4 ...
       if (tid >= (uint32_t)n_slabs || target >= total) {
         b = 0;  // the rest
       } else {
