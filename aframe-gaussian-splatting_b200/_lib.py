@@ -45,6 +45,7 @@ SYMBOLS = {
     "gs_destroy": (C.c_int, [_P]),
     "gs_last_error": (C.c_char_p, [_P]),
     "gs_version": (C.c_char_p, []),
+    "gs_bin_size": (C.c_uint32, []),
     "gs_clear": (C.c_int, [_P]),
     "gs_push_splats": (C.c_int, [_P, _P, C.c_uint32]),
     "gs_reserve": (C.c_int, [_P, C.c_uint32]),

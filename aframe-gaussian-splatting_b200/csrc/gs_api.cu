@@ -189,6 +189,8 @@ static void drop_graphs(gs_context *c) {
 // ---------------------------------------------------------------------------------------------
 // lifetime
 // ---------------------------------------------------------------------------------------------
+extern "C" uint32_t gs_bin_size(void) { return (uint32_t)kBin; }
+
 extern "C" const char *gs_version(void) { return "gsplat_b200 0.1 (sm_100a; restates aframe-gaussian-splatting index.js @ b50238f)"; }
 
 extern "C" const char *gs_last_error(const gs_context *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
@@ -583,7 +585,7 @@ static cudaError_t enqueue_bin_stage(gs_context *c, gs_context::Slot &sl, uint32
   if ((e = cudaMemsetAsync(b.bin_range, 0, sizeof(uint2) * (size_t)n_bins, m))) return e;
   if ((e = rec(sl.ev[2], m))) return e;
   launch_emit(c, sl.fp, sl.ctr, b, m);   // 2 launches (k_emit also histograms pass T1)
-  launch_tile_radix(c, sl.ctr, b, m);    // 5 launches
+  launch_tile_radix(c, sl.ctr, b, n_bins, m);    // 2 launches (<= 256 bins) or 5
   launch_tile_ranges(c, sl.ctr, b, m);
   if ((e = rec(sl.ev[3], m))) return e;
   return cudaGetLastError();
@@ -636,7 +638,7 @@ static int run_graph(gs_context *c, cudaGraphExec_t &ge, cudaStream_t stream, F 
 static int launch_frame(gs_context *c, gs_context::Slot &sl, bool reuse, uint32_t n_tiles, uint32_t n_bins) {
   // (re)capture when anything baked into the launches changed
   gs_context::GraphKey k;
-  k.cap = c->cap; k.n_tiles = n_tiles; k.cap_inst = c->cap_inst; k.p0 = c->depth; k.p1 = c->inst_rec[0]; k.p2 = c->center_scale;
+  k.cap = c->cap; k.n_tiles = n_tiles; k.n_bins = n_bins; k.cap_inst = c->cap_inst; k.p0 = c->depth; k.p1 = c->inst_rec[0]; k.p2 = c->center_scale;
   if (memcmp(&k, &c->gkey, sizeof(k)) != 0) {
     drop_graphs(c);
     c->gkey = k;
@@ -662,7 +664,7 @@ static int launch_frame(gs_context *c, gs_context::Slot &sl, bool reuse, uint32_
     // depth-tested / statistics frames use other instantiations of the raster: plain launches, no cached graph
     GS_CUDA(c, enqueue_raster_stage(c, sl, n_tiles, false));
   }
-  sl.launches = (reuse ? 0u : 7u) + 1u + 8u + 1u;
+  sl.launches = (reuse ? 0u : 7u) + 1u + (n_bins <= 256u ? 5u : 8u) + 1u;
   return GS_OK;
 }
 
@@ -705,7 +707,7 @@ static cudaError_t enqueue_slab_loop_stage(gs_context *c, gs_context::Slot &sl, 
     launch_project_entries(c, sl.fp, sl.ctr, b, st);      // vertex shader for the slab's entries
     if ((e = cudaMemsetAsync(b.bin_range, 0, sizeof(uint2) * (size_t)n_bins, st))) return e;
     launch_emit_slab(c, sl.fp, sl.ctr, b, st);
-    launch_tile_radix(c, sl.ctr, b, st);
+    launch_tile_radix(c, sl.ctr, b, n_bins, st);
     launch_tile_ranges(c, sl.ctr, b, st);
     if ((e = rec(sl.slab_ev[s][0], st))) return e;
     launch_raster_slab(c, sl.fp, sl.ctr, n_tiles, b, (sl.raster_flags & 2u) != 0, st);
@@ -725,7 +727,7 @@ static cudaError_t enqueue_slab_loop_stage(gs_context *c, gs_context::Slot &sl, 
 // (raster stream); stage A of frame k+1 runs under the loop of frame k (keys / slab table are double-buffered by set).
 static int launch_frame_slabs(gs_context *c, gs_context::Slot &sl, uint32_t n_tiles, uint32_t n_bins) {
   gs_context::GraphKey k;
-  k.cap = c->cap; k.n_tiles = n_tiles; k.cap_inst = c->cap_inst; k.p0 = c->depth; k.p1 = c->inst_rec[0]; k.p2 = c->center_scale;
+  k.cap = c->cap; k.n_tiles = n_tiles; k.n_bins = n_bins; k.cap_inst = c->cap_inst; k.p0 = c->depth; k.p1 = c->inst_rec[0]; k.p2 = c->center_scale;
   if (memcmp(&k, &c->gkey, sizeof(k)) != 0) {
     drop_graphs(c);
     c->gkey = k;
@@ -758,7 +760,7 @@ static int launch_frame_slabs(gs_context *c, gs_context::Slot &sl, uint32_t n_ti
   }
   GS_CUDA(c, cudaEventRecord(sl.ev_binned, c->rstream));
   c->sort_set_free[set] = sl.ev_binned;
-  sl.launches = 4u + 1u + (uint32_t)n_slabs * 21u + 2u;
+  sl.launches = 4u + 1u + (uint32_t)n_slabs * (n_bins <= 256u ? 18u : 21u) + 2u;
   return GS_OK;
 }
 

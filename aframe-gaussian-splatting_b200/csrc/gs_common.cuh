@@ -21,9 +21,11 @@ constexpr int kTile = 16;                 // 16x16 screen tiles (north_star): on
 // Binning granularity: splats are binned to 64x64-pixel BINS (4x4 tiles), not to tiles.  A splat meets ~4x fewer bins
 // than tiles, so the instance emission and the stable sort by bin id handle ~4x fewer elements; each tile's raster CTA
 // streams its bin's list and culls it against its own 16x16 pixels on the fly (exact footprint test, lane-parallel).
-constexpr int kBinShift = 6;
-constexpr int kBin = 1 << kBinShift;      // 64 pixels
-constexpr int kTilesPerBin = kBin / kTile;  // 4 tile columns / rows per bin
+#ifndef GS_BIN_TILES
+#define GS_BIN_TILES 4
+#endif
+constexpr int kTilesPerBin = GS_BIN_TILES;  // tile columns / rows per bin
+constexpr int kBin = kTile * kTilesPerBin;  // bin edge in pixels (64 by default; gs_bin_size() reports it)
 constexpr int kRadixThreads = 256;
 constexpr int kRadixItems = 16;
 constexpr int kRadixTile = kRadixThreads * kRadixItems;  // 4096 elements per look-back tile
@@ -256,7 +258,7 @@ struct gs_context {
   bool use_graphs = true;
   uint32_t raster_base_flags = 1;                // default pixel loop: 1 = packed fp32x2, 0 = scalar
   // graph cache key: anything baked into the captured launches
-  struct GraphKey { uint32_t cap = 0, n_tiles = 0; uint64_t cap_inst = 0; const void *p0 = nullptr, *p1 = nullptr, *p2 = nullptr; } gkey;
+  struct GraphKey { uint32_t cap = 0, n_tiles = 0, n_bins = 0, pad = 0; uint64_t cap_inst = 0; const void *p0 = nullptr, *p1 = nullptr, *p2 = nullptr; } gkey;
 
   // ---- fused exchange: one shared allocation per rank = flag rows + a ring of 3 frames, opened by every peer ----
   void *peer_local = nullptr;            // our shared block
@@ -295,7 +297,7 @@ void launch_depth_radix(gs_context *c, const FrameParams *fp, FrameCounters *ctr
 void launch_pack(gs_context *c, const uint8_t *rows_dev, uint32_t first, uint32_t n, cudaStream_t st);
 void launch_project(gs_context *c, const FrameParams *fp, const FrameBufs &b, cudaStream_t st);
 void launch_emit(gs_context *c, const FrameParams *fp, FrameCounters *ctr, const FrameBufs &b, cudaStream_t st);  // 2 launches
-void launch_tile_radix(gs_context *c, FrameCounters *ctr, const FrameBufs &b, cudaStream_t st);  // 5 launches
+void launch_tile_radix(gs_context *c, FrameCounters *ctr, const FrameBufs &b, uint32_t n_bins, cudaStream_t st);  // 2 or 5 launches
 void launch_tile_ranges(gs_context *c, FrameCounters *ctr, const FrameBufs &b, cudaStream_t st);
 void launch_raster(gs_context *c, const FrameParams *fp, uint32_t n_tiles, const FrameBufs &b, uint32_t flags, cudaStream_t st);
 void launch_peer_acquire(gs_context *c, const FrameParams *fp, FrameCounters *ctr, cudaStream_t st);

@@ -135,8 +135,8 @@ __global__ void __launch_bounds__(256) k_project(const float4 *__restrict__ cs, 
           fy1 = fminf(fy1, (float)rc.height - 1.0f);
           if (fx0 <= fx1 && fy0 <= fy1) {
             // rectangle of 64x64-pixel BINS (at most 64 per axis for frames up to 4096 px: never equals kNoRect)
-            const uint32_t tx0 = (uint32_t)fx0 >> kBinShift, tx1 = (uint32_t)fx1 >> kBinShift;
-            const uint32_t ty0 = (uint32_t)fy0 >> kBinShift, ty1 = (uint32_t)fy1 >> kBinShift;
+            const uint32_t tx0 = (uint32_t)fx0 / (uint32_t)kBin, tx1 = (uint32_t)fx1 / (uint32_t)kBin;
+            const uint32_t ty0 = (uint32_t)fy0 / (uint32_t)kBin, ty1 = (uint32_t)fy1 / (uint32_t)kBin;
             rect = tx0 | (tx1 << 8) | (ty0 << 16) | (ty1 << 24);
             // rgba stay packed (converted to float(byte)/255.0, index.js:152-157, once per record in the raster);
             // the last slot carries gl_Position.z/w (index.js:163) for the depth test against foreign geometry
@@ -349,9 +349,25 @@ __global__ void __launch_bounds__(kEmitThreads, 4) k_emit(const uint2 *__restric
       //  staged window dense); batches of 256 source entries until the staging arrays are full
       uint32_t nE = 0, jn = j0;
       while (jn <= j_last && nE + kEmitThreads <= (uint32_t)kEmitEnt) {
+        if ((jn & (uint32_t)(kEmitTile - 1)) == 0u) {
+          // at a slice boundary: skip runs of slices that own no instance at all (slab path after most bins have
+          // closed, or a rank that owns few of a region's bins) - 256 slices = 65536 entries per look
+          const uint32_t sl = (jn >> 8) + tid, sl_last = j_last >> 8;
+          const bool stop = (sl > sl_last) || (__ldg(slice_prefix + sl + 1) != __ldg(slice_prefix + sl));
+          const uint32_t bal0 = __ballot_sync(0xffffffffu, stop);
+          if (lane == 0) s_cnt[warp] = bal0 ? warp * 32u + (uint32_t)__ffs(bal0) - 1u : (uint32_t)kEmitThreads;
+          __syncthreads();
+          uint32_t skip = kEmitThreads;
+          for (uint32_t k2 = 0; k2 < kEmitThreads / 32; ++k2) skip = min(skip, s_cnt[k2]);
+          __syncthreads();  // s_cnt is reused by the batch below
+          jn += skip * (uint32_t)kEmitTile;
+          if (skip == (uint32_t)kEmitThreads) continue;
+          if (jn > j_last) break;
+        }
+        const uint32_t jend = (jn | (uint32_t)(kEmitTile - 1)) + 1u;  // batches end at slice boundaries
         const uint32_t j = jn + tid;
         uint2 en = make_uint2(0u, kNoRect);
-        if (j <= j_last) en = __ldg(ent + j);
+        if (j < jend && j <= j_last) en = __ldg(ent + j);
         const bool nz = en.y != kNoRect;
         const uint32_t bal = __ballot_sync(0xffffffffu, nz);
         if (lane == 0) s_cnt[warp] = __popc(bal);
@@ -373,7 +389,7 @@ __global__ void __launch_bounds__(kEmitThreads, 4) k_emit(const uint2 *__restric
           }
         }
         nE += tot;
-        jn += kEmitThreads;
+        jn = jend;
         __syncthreads();
       }
       const uint32_t jE = min(jn, j_last + 1);

@@ -232,20 +232,26 @@ __global__ void __launch_bounds__(kCompactThreads) k_compact_count(const uint32_
   }
 }
 
-// exclusive scan of the chunk counts, one CTA
+// exclusive scan of the chunk counts, one CTA; every thread owns 16 consecutive counts per round
 __global__ void __launch_bounds__(1024) k_compact_scan(uint32_t *__restrict__ cnt, const FrameParams *__restrict__ fp,
                                                        const FrameCounters *__restrict__ ctr) {
   if (!ctr->slab_real) return;
+  constexpr uint32_t kPer = 16;
   __shared__ uint32_t s_w[32];
   __shared__ uint32_t s_carry;
   const uint32_t nchunks = (fp->n_splats + kCompactChunk - 1) / kCompactChunk;
   const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
   if (tid == 0) s_carry = 0;
   __syncthreads();
-  for (uint32_t b = 0; b < nchunks; b += 1024) {
-    const uint32_t i = b + tid;
-    const uint32_t v = i < nchunks ? cnt[i] : 0u;
-    uint32_t incl = v;
+  for (uint32_t b = 0; b < nchunks; b += 1024 * kPer) {
+    const uint32_t i0 = b + tid * kPer;
+    uint32_t v[kPer], sum = 0;
+#pragma unroll
+    for (uint32_t k = 0; k < kPer; ++k) {
+      v[k] = (i0 + k < nchunks) ? cnt[i0 + k] : 0u;
+      sum += v[k];
+    }
+    uint32_t incl = sum;
     for (int o = 1; o < 32; o <<= 1) {
       const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
       if (lane >= (uint32_t)o) incl += t;
@@ -255,7 +261,12 @@ __global__ void __launch_bounds__(1024) k_compact_scan(uint32_t *__restrict__ cn
     uint32_t wb = 0;
     for (uint32_t w = 0; w < warp; ++w) wb += s_w[w];
     const uint32_t carry = s_carry;
-    if (i < nchunks) cnt[i] = carry + wb + incl - v;
+    uint32_t run = carry + wb + incl - sum;
+#pragma unroll
+    for (uint32_t k = 0; k < kPer; ++k) {
+      if (i0 + k < nchunks) cnt[i0 + k] = run;
+      run += v[k];
+    }
     __syncthreads();
     if (tid == 1023) s_carry = carry + wb + incl;
     __syncthreads();

@@ -121,6 +121,8 @@ struct RadixArgs {
   // slab path: compacted (key, index) pairs of the current slab
   const uint16_t *ckey;
   const uint32_t *cidx;
+  // frames of at most 256 bins: the bin id is one byte, pass T1 is the whole sort and gathers the records itself
+  uint32_t t1_final;
 };
 
 template <int PASS>
@@ -371,8 +373,16 @@ __global__ void __launch_bounds__(kScatThreads, 2) k_radix_scatter(RadixArgs a) 
       } else if (PASS == PASS_D2) {
         a.order[pos] = p;
       } else if (PASS == PASS_T1) {
-        a.inst_idx_b[pos] = p;
-        a.inst_tile_b[pos] = s_hi[i];
+        if (a.t1_final) {
+          const float4 r0 = __ldg(a.proj_rec + 2 * (size_t)p);
+          const float4 r1 = __ldg(a.proj_rec + 2 * (size_t)p + 1);
+          a.inst_rec[2 * (size_t)pos] = r0;
+          a.inst_rec[2 * (size_t)pos + 1] = r1;
+          a.inst_tile_f[pos] = s_hi[i];
+        } else {
+          a.inst_idx_b[pos] = p;
+          a.inst_tile_b[pos] = s_hi[i];
+        }
       } else {
         const float4 r0 = __ldg(a.proj_rec + 2 * (size_t)p);
         const float4 r1 = __ldg(a.proj_rec + 2 * (size_t)p + 1);
@@ -449,13 +459,14 @@ void launch_depth_radix(gs_context *c, const FrameParams *fp, FrameCounters *ctr
 
 // stable sort of the tile instances by tile id (5 launches: T1's histogram is produced by k_emit);
 // T2 writes the per-tile record lists
-void launch_tile_radix(gs_context *c, FrameCounters *ctr, const FrameBufs &b, cudaStream_t st) {
+void launch_tile_radix(gs_context *c, FrameCounters *ctr, const FrameBufs &b, uint32_t n_bins, cudaStream_t st) {
   RadixArgs a = make_args(c, nullptr, ctr, b);
   a.table = c->table_d;
   a.totals = c->totals + 256;
   a.stride = c->table_d_stride;
+  a.t1_final = n_bins <= 256u ? 1u : 0u;  // one byte of bin id: T1 alone sorts (and gathers the records)
   run_pass<PASS_T1>(c, a, c->cap_inst, st);
-  run_pass<PASS_T2>(c, a, c->cap_inst, st);
+  if (!a.t1_final) run_pass<PASS_T2>(c, a, c->cap_inst, st);
 }
 
 // slab path: stable sort of the compacted slab by its 16-bit key (6 launches) -> b.order = the slab's draw order

@@ -19,7 +19,13 @@ from typing import Callable, Optional
 import numpy as np
 
 TILE = 16
-BIN_TILES = 4  # tile columns per 64-pixel bin column
+
+
+def bin_tiles() -> int:
+    """tile columns per bin column: gs_bin_size() / 16 (4 for the default 64-pixel bins)"""
+    from . import _lib
+    return int(_lib.load().gs_bin_size()) // TILE
+
 
 
 @dataclass(frozen=True)
@@ -38,20 +44,22 @@ class TileSharding:
 
     def owner(self, tx: int, ty: int) -> int:
         """rank r owns the 64-pixel bin columns bx = tx // 4 with bx % world == r (csrc/gs_common.cuh owned_*)"""
-        return (tx // BIN_TILES) % self.world
+        return (tx // bin_tiles()) % self.world
 
     def owned_cols(self, rank: int) -> int:
         """owned TILE columns: 4 per owned bin column, fewer in a partial last bin column (owned_tile_cols)"""
-        full, rem = divmod(self.tiles_x, BIN_TILES)
-        n = BIN_TILES * ((full - 1 - rank) // self.world + 1 if rank < full else 0)
+        bt = bin_tiles()
+        full, rem = divmod(self.tiles_x, bt)
+        n = bt * ((full - 1 - rank) // self.world + 1 if rank < full else 0)
         if rem and full % self.world == rank:
             n += rem
         return n
 
     def slot(self, tx: int, ty: int, rank: int) -> int:
         """index of tile (tx, ty) inside rank's packed tile buffer (mirrors owned_slot)."""
-        bx = tx // BIN_TILES
-        return ty * self.owned_cols(rank) + (bx - rank) // self.world * BIN_TILES + tx % BIN_TILES
+        bt = bin_tiles()
+        bx = tx // bt
+        return ty * self.owned_cols(rank) + (bx - rank) // self.world * bt + tx % bt
 
     def owned_tiles(self, rank: int) -> int:
         return self.tiles_y * self.owned_cols(rank)

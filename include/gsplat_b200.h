@@ -102,6 +102,9 @@ GS_API int gs_destroy(gs_context *ctx);
 /* Last error text of this context (or of the failed gs_create when ctx == NULL). */
 GS_API const char *gs_last_error(const gs_context *ctx);
 GS_API const char *gs_version(void);
+/* Edge, in pixels, of the square screen bins splats are binned to (a multiple of the 16-pixel raster tile; 64 unless the
+ * library was built with another GS_BIN_TILES).  Multi-GPU tile ownership is by bin column (gs_set_shard). */
+GS_API uint32_t gs_bin_size(void);
 
 /* ---- seam 1: the worker message protocol (index.js:572-598) ------------------------------ */
 

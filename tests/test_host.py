@@ -44,10 +44,11 @@ def test_owned_tiles_partition(gs):
         tiles = ((w + 15) // 16) * ((h + 15) // 16)
         for world in (1, 2, 3, 4, 8):
             counts = [lib.gs_owned_tiles(w, h, r, world) for r in range(world)]
-            assert sum(counts) == tiles and max(counts) - min(counts) <= 4 * ((h + 15) // 16)
+            bt = gs.dist.bin_tiles()  # tile columns per bin column (gs_bin_size() / 16)
+            assert sum(counts) == tiles and max(counts) - min(counts) <= bt * ((h + 15) // 16)
             tx, ty = np.meshgrid(np.arange((w + 15) // 16), np.arange((h + 15) // 16))
-            for r in range(world):  # rank r owns the 64-pixel bin columns bx = tx // 4 with bx % world == r
-                assert counts[r] == int((((tx // 4) % world) == r).sum())
+            for r in range(world):  # rank r owns the bin columns bx = tx // bt with bx % world == r
+                assert counts[r] == int((((tx // bt) % world) == r).sum())
 
 
 def test_synth_is_deterministic_and_ordered(gs):
