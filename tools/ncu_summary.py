@@ -43,7 +43,7 @@ def launches(src, dst):
     agg = collections.OrderedDict()
     for d in data:
         agg.setdefault(d["Kernel Name"].split("(")[0], []).append(float(d["Metric Value"].replace(",", "")) / 1000.0)
-    ours = {k: v for k, v in agg.items() if "gs::" in k}
+    ours = {k: v for k, v in agg.items() if ("gs::" in k or "k_" in k) and "at::" not in k}
     per_frame = sum(sum(v) / len(v) for v in ours.values())
     with open(dst, "w") as f:
         f.write(f"# ncu launch list ({os.path.basename(src)}): gpu__time_duration.sum per launch, --clock-control none\n\n")
