@@ -585,8 +585,7 @@ static cudaError_t enqueue_bin_stage(gs_context *c, gs_context::Slot &sl, uint32
   if ((e = cudaMemsetAsync(b.bin_range, 0, sizeof(uint2) * (size_t)n_bins, m))) return e;
   if ((e = rec(sl.ev[2], m))) return e;
   launch_emit(c, sl.fp, sl.ctr, b, m);   // 2 launches (k_emit also histograms pass T1)
-  launch_tile_radix(c, sl.ctr, b, n_bins, m);    // 2 launches (<= 256 bins) or 5
-  launch_tile_ranges(c, sl.ctr, b, m);
+  launch_tile_radix(c, sl.ctr, b, n_bins, m);    // 2 launches (<= 256 bins) or 6 (incl. k_tile_ranges)
   if ((e = rec(sl.ev[3], m))) return e;
   return cudaGetLastError();
 }
@@ -664,7 +663,7 @@ static int launch_frame(gs_context *c, gs_context::Slot &sl, bool reuse, uint32_
     // depth-tested / statistics frames use other instantiations of the raster: plain launches, no cached graph
     GS_CUDA(c, enqueue_raster_stage(c, sl, n_tiles, false));
   }
-  sl.launches = (reuse ? 0u : 7u) + 1u + (n_bins <= 256u ? 5u : 8u) + 1u;
+  sl.launches = (reuse ? 0u : 7u) + 1u + (n_bins <= 256u ? 4u : 8u) + 1u;
   return GS_OK;
 }
 
@@ -708,7 +707,6 @@ static cudaError_t enqueue_slab_loop_stage(gs_context *c, gs_context::Slot &sl, 
     if ((e = cudaMemsetAsync(b.bin_range, 0, sizeof(uint2) * (size_t)n_bins, st))) return e;
     launch_emit_slab(c, sl.fp, sl.ctr, b, st);
     launch_tile_radix(c, sl.ctr, b, n_bins, st);
-    launch_tile_ranges(c, sl.ctr, b, st);
     if ((e = rec(sl.slab_ev[s][0], st))) return e;
     launch_raster_slab(c, sl.fp, sl.ctr, n_tiles, b, (sl.raster_flags & 2u) != 0, st);
     if ((e = rec(sl.slab_ev[s][1], st))) return e;
@@ -760,7 +758,7 @@ static int launch_frame_slabs(gs_context *c, gs_context::Slot &sl, uint32_t n_ti
   }
   GS_CUDA(c, cudaEventRecord(sl.ev_binned, c->rstream));
   c->sort_set_free[set] = sl.ev_binned;
-  sl.launches = 4u + 1u + (uint32_t)n_slabs * (n_bins <= 256u ? 18u : 21u) + 2u;
+  sl.launches = 4u + 1u + (uint32_t)n_slabs * (n_bins <= 256u ? 17u : 21u) + 2u;
   return GS_OK;
 }
 

@@ -123,6 +123,8 @@ struct RadixArgs {
   const uint32_t *cidx;
   // frames of at most 256 bins: the bin id is one byte, pass T1 is the whole sort and gathers the records itself
   uint32_t t1_final;
+  uint2 *bin_range;   // t1_final: the per-bin {start, end} fall out of the digit totals (no k_tile_ranges launch)
+  uint32_t n_bins;
 };
 
 template <int PASS>
@@ -294,7 +296,9 @@ __global__ void __launch_bounds__(kScatThreads, 2) k_radix_scatter(RadixArgs a) 
   };
 
   // first output slot of each digit
-  const uint32_t dbase = scan256(tid < 256 ? a.totals[tid] : 0u);
+  const uint32_t dtot = tid < 256 ? a.totals[tid] : 0u;
+  const uint32_t dbase = scan256(dtot);
+  if (PASS == PASS_T1 && a.t1_final && blockIdx.x == 0 && tid < a.n_bins) a.bin_range[tid] = make_uint2(dbase, dbase + dtot);
   DepthRange dr{0.0, 0.0};
   if (PASS == PASS_D1) dr = load_depth_range(ctr);
 
@@ -378,7 +382,6 @@ __global__ void __launch_bounds__(kScatThreads, 2) k_radix_scatter(RadixArgs a) 
           const float4 r1 = __ldg(a.proj_rec + 2 * (size_t)p + 1);
           a.inst_rec[2 * (size_t)pos] = r0;
           a.inst_rec[2 * (size_t)pos + 1] = r1;
-          a.inst_tile_f[pos] = s_hi[i];
         } else {
           a.inst_idx_b[pos] = p;
           a.inst_tile_b[pos] = s_hi[i];
@@ -457,6 +460,8 @@ void launch_depth_radix(gs_context *c, const FrameParams *fp, FrameCounters *ctr
   run_pass<PASS_D2>(c, a, c->cap, st);
 }
 
+void launch_tile_ranges(gs_context *c, FrameCounters *ctr, const FrameBufs &b, cudaStream_t st);
+
 // stable sort of the tile instances by tile id (5 launches: T1's histogram is produced by k_emit);
 // T2 writes the per-tile record lists
 void launch_tile_radix(gs_context *c, FrameCounters *ctr, const FrameBufs &b, uint32_t n_bins, cudaStream_t st) {
@@ -464,9 +469,14 @@ void launch_tile_radix(gs_context *c, FrameCounters *ctr, const FrameBufs &b, ui
   a.table = c->table_d;
   a.totals = c->totals + 256;
   a.stride = c->table_d_stride;
-  a.t1_final = n_bins <= 256u ? 1u : 0u;  // one byte of bin id: T1 alone sorts (and gathers the records)
+  a.t1_final = n_bins <= 256u ? 1u : 0u;  // one byte of bin id: T1 alone sorts, gathers the records and writes the ranges
+  a.bin_range = b.bin_range;
+  a.n_bins = n_bins;
   run_pass<PASS_T1>(c, a, c->cap_inst, st);
-  if (!a.t1_final) run_pass<PASS_T2>(c, a, c->cap_inst, st);
+  if (!a.t1_final) {
+    run_pass<PASS_T2>(c, a, c->cap_inst, st);
+    launch_tile_ranges(c, ctr, b, st);
+  }
 }
 
 // slab path: stable sort of the compacted slab by its 16-bit key (6 launches) -> b.order = the slab's draw order
