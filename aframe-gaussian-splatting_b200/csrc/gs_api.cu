@@ -182,7 +182,7 @@ static void drop_graphs(gs_context *c) {
   for (auto &sl : c->slot)
     for (int i = 0; i < 2; ++i) {
       kill(sl.graph_a[i][0]); kill(sl.graph_a[i][1]); kill(sl.graph_b[i]); kill(sl.graph_r[i]); kill(sl.graph_rp[i]);
-      kill(sl.graph_sa[i]); kill(sl.graph_sl[i][0]); kill(sl.graph_sl[i][1]);
+      kill(sl.graph_sa[i]); kill(sl.graph_sl[i][0]); kill(sl.graph_sl[i][1]); kill(sl.graph_sl[i][2]);
     }
 }
 
@@ -736,7 +736,7 @@ static int launch_frame_slabs(gs_context *c, gs_context::Slot &sl, uint32_t n_ti
   while (n_slabs < kMaxSlabs && slab_cumulative(c->slab_first, n_slabs) < sl.n_splats) ++n_slabs;
   if (n_slabs != sl.graph_slabs[set]) {  // the captured loop bakes the slab count
     auto kill = [](cudaGraphExec_t &g) { if (g) { cudaGraphExecDestroy(g); g = nullptr; } };
-    kill(sl.graph_sa[set]); kill(sl.graph_sl[set][0]); kill(sl.graph_sl[set][1]);
+    kill(sl.graph_sa[set]); kill(sl.graph_sl[set][0]); kill(sl.graph_sl[set][1]); kill(sl.graph_sl[set][2]);
     sl.graph_slabs[set] = n_slabs;
   }
   sl.n_slabs = n_slabs;
@@ -750,9 +750,11 @@ static int launch_frame_slabs(gs_context *c, gs_context::Slot &sl, uint32_t n_ti
   GS_CUDA(c, cudaEventRecord(sl.ev_sorted, c->stream));
   // loop: needs A of this frame; consecutive loops are ordered by the stream itself
   GS_CUDA(c, cudaStreamWaitEvent(c->rstream, sl.ev_sorted, 0));
-  if (sl.peer) {
+  // graph variants of the loop: [plain, depth-tested, fused peer exchange]
+  const int variant = sl.peer ? 2 : ((sl.raster_flags & 2u) ? 1 : 0);
+  if (sl.peer && (sl.raster_flags & 2u)) {  // depth-tested peer frames: rare, plain launches
     GS_CUDA(c, enqueue_slab_loop_stage(c, sl, n_tiles, n_bins, false));
-  } else if ((rc = run_graph(c, sl.graph_sl[set][(sl.raster_flags & 2u) ? 1 : 0], c->rstream,
+  } else if ((rc = run_graph(c, sl.graph_sl[set][variant], c->rstream,
                              [&](bool ext) { return enqueue_slab_loop_stage(c, sl, n_tiles, n_bins, ext); }))) {
     return rc;
   }

@@ -220,7 +220,7 @@ struct gs_context {
     cudaGraphExec_t graph_r[2] = {nullptr, nullptr};                           // raster, [set]
     cudaGraphExec_t graph_rp[2] = {nullptr, nullptr};                          // acquire + raster + signal/wait (fused exchange)
     cudaGraphExec_t graph_sa[2] = {nullptr, nullptr};                          // slab path: keys stage, [set]
-    cudaGraphExec_t graph_sl[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};  // slab path: slab loop + resolve, [set][depth]
+    cudaGraphExec_t graph_sl[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};  // slab path: slab loop + resolve, [set][plain | depth | peer]
     int graph_slabs[2] = {0, 0};                                               // slab count baked into graph_sl
     bool peer = false;
     uint64_t ticket = 0;
