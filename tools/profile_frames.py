@@ -25,6 +25,7 @@ def main():
     ap.add_argument("--warm", type=int, default=3)
     ap.add_argument("--splats", type=int, default=0)
     ap.add_argument("--stats", action="store_true", help="render GS_RENDER_STATS frames")
+    ap.add_argument("--shard", default="", help="rank/world: render only this rank's share of the frame (tile-sharded mode on one GPU)")
     args = ap.parse_args()
     sc = gs.scenes
     n, w, h, seed, cutout = sc.CONFIGS[args.workload]
@@ -36,6 +37,9 @@ def main():
     else:
         frames = [sc.make_frame(sc.fixed_camera(w, h), sc.demo_object(), w, h, sc.demo_cutout() if cutout else None)]
     ctx = gs.SplatContext(0)
+    if args.shard:
+        r, wd = (int(v) for v in args.shard.split("/"))
+        ctx.set_shard(r, wd)
     ctx.reserve(n)
     for first in range(0, n, 4 << 20):
         ctx.push_splats(rows[first:first + (4 << 20)])
