@@ -31,7 +31,7 @@ constexpr int kTilesPerBin = GS_BIN_TILES;  // tile columns / rows per bin
 constexpr int kBin = kTile * kTilesPerBin;  // bin edge in pixels (96 by default; gs_bin_size() reports it)
 constexpr int kRadixThreads = 256;
 constexpr int kRadixItems = 16;
-constexpr int kRadixTile = kRadixThreads * kRadixItems;  // 4096 elements per look-back tile
+constexpr int kRadixTile = kRadixThreads * kRadixItems;  // 4096 elements per radix chunk
 constexpr int kEmitThreads = 256;
 constexpr int kEmitItems = 1;
 constexpr int kEmitTile = kEmitThreads * kEmitItems;      // 256 draw-order entries per slice of the instance-offset scan
@@ -344,7 +344,7 @@ __host__ __device__ inline double dec_f64(unsigned long long e) {
 #endif
 }
 
-// Exact footprint-vs-box test shared by the bin emission (64x64 box) and the raster's cull (16x16 box).
+// Exact footprint-vs-box test shared by the bin emission (kBin x kBin box) and the raster's cull (16x16 box).
 // The box holds pixel CENTRES [x0, x0 + extent] x [y0, y0 + extent]; the footprint is the set r^2 = px^2 + py^2 <= 4 with
 // (px, py) = (d.a2, d.a1), d = sample - centre (index.js:158-172).  r^2 is a convex quadratic of d, so when the centre
 // lies outside the box its minimum over the box is attained on the edge(s) facing the centre; the test evaluates those
@@ -375,7 +375,7 @@ __device__ __forceinline__ bool footprint_meets_box(float cx, float cy, float a1
   return !(qmin > 4.02f);  // NaN keeps
 }
 
-// ---- multi-GPU ownership: rank r owns the BIN COLUMNS bx with bx % world == r (64-pixel wide vertical stripes,
+// ---- multi-GPU ownership: rank r owns the BIN COLUMNS bx with bx % world == r (kBin-pixel wide vertical stripes,
 // interleaved), so the owned bins of any bin rectangle have a closed form; a tile belongs to the owner of its bin ----
 __host__ __device__ inline uint32_t owned_cols(uint32_t bins_x, uint32_t rank, uint32_t world) {
   return rank < bins_x ? (bins_x - 1 - rank) / world + 1 : 0u;

@@ -1,5 +1,5 @@
 // gs_project.cu — per-splat projection (the reference's vertex shader, index.js:101-164) and the
-// ordered emission of bin instances (64x64-pixel bins = 4x4 raster tiles; "tile" below means bin).
+// ordered emission of bin instances (kBin x kBin-pixel bins = 6x6 raster tiles by default; "tile" below means bin).
 //
 //   k_project  : fp32 restatement of the vertex shader, op for op (no FMA contraction), producing a
 //                32 B projected record per splat + its packed tile rectangle.
@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(256) k_project(const float4 *__restrict__ cs, 
           fx1 = fminf(fx1, (float)rc.width - 1.0f);
           fy1 = fminf(fy1, (float)rc.height - 1.0f);
           if (fx0 <= fx1 && fy0 <= fy1) {
-            // rectangle of 64x64-pixel BINS (at most 64 per axis for frames up to 4096 px: never equals kNoRect)
+            // rectangle of BINS (at most 43 per axis for frames up to 4096 px at 96 px: never equals kNoRect)
             const uint32_t tx0 = (uint32_t)fx0 / (uint32_t)kBin, tx1 = (uint32_t)fx1 / (uint32_t)kBin;
             const uint32_t ty0 = (uint32_t)fy0 / (uint32_t)kBin, ty1 = (uint32_t)fy1 / (uint32_t)kBin;
             rect = tx0 | (tx1 << 8) | (ty0 << 16) | (ty1 << 24);

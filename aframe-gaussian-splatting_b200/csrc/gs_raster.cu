@@ -1,7 +1,7 @@
 // gs_raster.cu — one CTA per 16x16 tile: the reference's fragment shader (index.js:170-175) and its
 // blend state (index.js:177-181), composited front-to-back with transmittance.
 //
-// Splats are binned to 64x64-pixel bins (4x4 tiles): the range [bin_range[b].x, bin_range[b].y) of inst_rec holds
+// Splats are binned to kBin x kBin-pixel bins (96 px = 6x6 tiles by default): the range [bin_range[b].x, bin_range[b].y) of inst_rec holds
 // the 32 B projected records of bin b, contiguous, in back-to-front draw order.  A tile's CTA pulls its bin's range
 // with 1-D TMA bulk copies (cp.async.bulk.shared::cluster.global + mbarrier complete_tx) through a shared-memory
 // ring, nearest chunk first, and for every chunk

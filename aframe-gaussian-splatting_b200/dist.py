@@ -1,7 +1,7 @@
 """Multi-GPU frame sharding: one process per GPU, torch.distributed for the plumbing.
 
 The reference has no multi-GPU path (one worker + one GL context).  Here the FRAME is sharded, not the splat
-table: rank r rasters the 64-pixel BIN columns bx with bx % world == r (a bin = 4x4 tiles of 16x16 pixels, the
+table: rank r rasters the BIN columns bx with bx % world == r (a bin = 6x6 tiles of 16x16 pixels = 96 px by default, the
 granularity splats are binned at).  Every rank keeps the full 36 B/splat table
 in its own HBM (80 M splats = 2.9 GB of 180 GB) and computes the same global draw order, so every pixel is
 composited on exactly one GPU in exactly the reference's order - the sharded frame is bit-identical to the
@@ -22,7 +22,7 @@ TILE = 16
 
 
 def bin_tiles() -> int:
-    """tile columns per bin column: gs_bin_size() / 16 (4 for the default 64-pixel bins)"""
+    """tile columns per bin column: gs_bin_size() / 16 (6 for the default 96-pixel bins)"""
     from . import _lib
     return int(_lib.load().gs_bin_size()) // TILE
 
@@ -43,7 +43,7 @@ class TileSharding:
         return (self.height + TILE - 1) // TILE
 
     def owner(self, tx: int, ty: int) -> int:
-        """rank r owns the 64-pixel bin columns bx = tx // 4 with bx % world == r (csrc/gs_common.cuh owned_*)"""
+        """rank r owns the bin columns bx = tx // bin_tiles() with bx % world == r (csrc/gs_common.cuh owned_*)"""
         return (tx // bin_tiles()) % self.world
 
     def owned_cols(self, rank: int) -> int:

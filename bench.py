@@ -59,7 +59,7 @@ def load_peaks():
 def algorithmic_bytes(st: dict) -> dict:
     """SURVEY.md 8(d) per-frame algorithmic bytes, from the counters the library returns."""
     # D = 16x16 tile instances whose tile really meets the r<=2 footprint (SURVEY.md 8: "D = sum of 16x16 tiles touched"),
-    # counted exactly by a GS_RENDER_STATS frame.  The library itself bins to 64x64-pixel bins (~4x fewer instances) and
+    # counted exactly by a GS_RENDER_STATS frame.  The library itself bins to 96x96-pixel bins (~5x fewer instances) and
     # culls per tile inside the raster, so it MOVES fewer bytes than this formula charges.
     N, V, V2, D, T = st["n_splats"], st["n_sorted"], st["n_visible"], st["n_tile_instances"], st["n_tiles"]
     P = st["width"] * st["height"]

@@ -85,9 +85,9 @@ typedef struct gs_stats {
   float ms_total;          /* first kernel to last kernel of this frame on the device; with several
                               frames in flight it includes waiting behind the previous raster  */
   uint32_t kernel_launches;/* kernels launched by the call                                   */
-  uint32_t n_instances_kept;/*    BIN instances kept: 64x64-pixel bins really meeting the r<=2 footprint.
+  uint32_t n_instances_kept;/*    BIN instances kept: screen bins (gs_bin_size(), 96 px) really meeting the r<=2 footprint.
                                   (n_instances counts the bounding-rectangle candidates.)  Splats are binned
-                                  to 64x64 bins; each 16x16 tile culls its bin's list in the raster.        */
+                                  to bins; each 16x16 tile culls its bin's list in the raster.               */
   uint64_t n_tile_instances;/* D  (STATS) 16x16 tiles meeting the footprint, summed over the drawn splats     */
   uint64_t n_records_streamed;/*  (STATS) bin records the raster CTAs pulled through shared memory            */
   uint64_t n_pair_tests;    /*    (STATS) pixel-splat pairs evaluated by live pixels                          */

@@ -119,7 +119,7 @@ def test_stats_frame_counts(gs, orc, ctx):
         pairs += int(msk.sum())
     # the cull is conservative (0.5 % slack, closest point on the tile box): it may keep a few tiles no pixel centre covers
     assert exact <= st["n_tile_instances"] <= exact * 1.05 + 16
-    assert st["n_instances_kept"] < st["n_tile_instances"]            # 64x64 bins: fewer instances than tiles
+    assert st["n_instances_kept"] < st["n_tile_instances"]            # bins are coarser than tiles: fewer instances
     assert st["n_records_streamed"] >= st["n_tile_instances"]
     assert 0 < st["n_pair_hits"] <= st["n_pair_tests"]
     assert st["n_pair_hits"] <= pairs * 1.001 + 16                     # early-stopped pixels skip pairs, never add any
