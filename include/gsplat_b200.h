@@ -55,7 +55,10 @@ enum {
   GS_RENDER_OUT_DEVICE = 1u << 0, /* out_rgba is a device pointer on the context's GPU        */
   GS_RENDER_REUSE_SORT = 1u << 1, /* reuse the draw order of the previous gs_sort/gs_render
                                      (reference behaviour when sortReady is false,
-                                     index.js:206,439-440: the draw uses a stale order)       */
+                                     index.js:206,439-440: the draw uses a stale order).  Frames
+                                     that sort >= 16 M splats are rendered front to back in depth
+                                     slabs and leave no complete order behind: after such a frame
+                                     the flag is ignored (the frame sorts) unless gs_sort ran since */
   GS_RENDER_OUT_TILED = 1u << 2,  /* multi-GPU: write only the tiles this rank owns, packed as
                                      16x16 RGBA blocks in owned-tile order (see gs_set_shard) */
   GS_RENDER_OUT_PEER = 1u << 3,   /* multi-GPU, fused raster + exchange: every finished tile is stored
