@@ -339,7 +339,7 @@ def test_slab_path_random_regimes(gs, orc, ctx, monkeypatch):
         for variant in ("plain", "cutout", "behind"):
             if variant == "behind":  # camera looks away from the scene: nothing passes the worker filter or the clip
                 cam = gs.three_math.PerspectiveCamera(fov=80.0, aspect=w / h, near=0.005, far=10000.0, position=(0.0, 1.6, 40.0),
-                                                      quaternion=gs.three_math.yaw_quaternion(0.0))
+                                                      quaternion=gs.three_math.yaw_quaternion(np.pi))
                 fr = sc.make_frame(cam, sc.demo_object(), w, h)
             else:
                 cam = sc.orbit_camera(w, h, int(rng.integers(0, 120)))
