@@ -585,7 +585,7 @@ static cudaError_t enqueue_bin_stage(gs_context *c, gs_context::Slot &sl, uint32
   if ((e = cudaMemsetAsync(b.bin_range, 0, sizeof(uint2) * (size_t)n_bins, m))) return e;
   if ((e = rec(sl.ev[2], m))) return e;
   launch_emit(c, sl.fp, sl.ctr, b, m);   // 2 launches (k_emit also histograms pass T1)
-  launch_tile_radix(c, sl.ctr, b, n_bins, m);    // 2 launches (<= 256 bins) or 6 (incl. k_tile_ranges)
+  launch_tile_radix(c, sl.ctr, b, n_bins, false, m);    // 2 launches (<= 256 bins) or 6 (incl. k_tile_ranges)
   if ((e = rec(sl.ev[3], m))) return e;
   return cudaGetLastError();
 }
@@ -706,7 +706,7 @@ static cudaError_t enqueue_slab_loop_stage(gs_context *c, gs_context::Slot &sl, 
     launch_project_entries(c, sl.fp, sl.ctr, b, st);      // vertex shader for the slab's entries
     if ((e = cudaMemsetAsync(b.bin_range, 0, sizeof(uint2) * (size_t)n_bins, st))) return e;
     launch_emit_slab(c, sl.fp, sl.ctr, b, st);
-    launch_tile_radix(c, sl.ctr, b, n_bins, st);
+    launch_tile_radix(c, sl.ctr, b, n_bins, true, st);  // k_emit_entries leaves T1's histogram to its own kernel
     if ((e = rec(sl.slab_ev[s][0], st))) return e;
     launch_raster_slab(c, sl.fp, sl.ctr, n_tiles, b, (sl.raster_flags & 2u) != 0, st);
     if ((e = rec(sl.slab_ev[s][1], st))) return e;
@@ -760,7 +760,7 @@ static int launch_frame_slabs(gs_context *c, gs_context::Slot &sl, uint32_t n_ti
   }
   GS_CUDA(c, cudaEventRecord(sl.ev_binned, c->rstream));
   c->sort_set_free[set] = sl.ev_binned;
-  sl.launches = 4u + 1u + (uint32_t)n_slabs * (n_bins <= 256u ? 17u : 21u) + 2u;
+  sl.launches = 4u + 1u + (uint32_t)n_slabs * (n_bins <= 256u ? 18u : 22u) + 2u;
   return GS_OK;
 }
 

@@ -505,6 +505,96 @@ __global__ void __launch_bounds__(kEmitThreads, 4) k_emit(const uint2 *__restric
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// K3b', slab path: instance emission by ENTRY.  In a slab most entries own nothing any more (closed bins, other
+// ranks' bins), so the instance-window walk of k_emit would spend its time stepping over dead entries; here one thread
+// owns one live entry and writes its instances at the entry's own offset (position = prefix(entry) + k, so the array is
+// still in draw order).  Entries with large rectangles are finished by their whole warp, 32 candidates per step.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void emit_candidate(const RenderConsts &rc, uint32_t bx, uint32_t by, bool multi, const float4 &r0,
+                                               const float2 &r1, const uint32_t *__restrict__ bin_open, uint32_t payload,
+                                               size_t pos, uint16_t *__restrict__ inst_tile, uint32_t *__restrict__ inst_idx) {
+  bool keep = true;
+  if (multi)
+    keep = footprint_meets_box(r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, (float)(bx * kBin) + 0.5f, (float)(by * kBin) + 0.5f,
+                               (float)(kBin - 1));
+  const uint32_t t = by * rc.bins_x + bx;
+  if (keep && bin_open) keep = __ldg(bin_open + t) != 0u;
+  inst_tile[pos] = keep ? (uint16_t)t : kNoTile;
+  inst_idx[pos] = payload;
+}
+
+__global__ void __launch_bounds__(256) k_emit_entries(const uint2 *__restrict__ ent, const uint32_t *__restrict__ ent_off,
+                                                      const uint32_t *__restrict__ slice_prefix,
+                                                      const float4 *__restrict__ proj_rec, const FrameParams *__restrict__ fp,
+                                                      uint64_t cap_inst, uint16_t *__restrict__ inst_tile,
+                                                      uint32_t *__restrict__ inst_idx, FrameCounters *ctr,
+                                                      const uint32_t *__restrict__ bin_open) {
+  const RenderConsts &rc = fp->rc;
+  const uint32_t nv = ctr->sort.n_valid;
+  if (ctr->n_inst > cap_inst) {  // instance buffer too small: the host regrows it and re-runs the frame
+    if (blockIdx.x == 0 && threadIdx.x == 0) ctr->overflow = 1u;
+    return;
+  }
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t stride = gridDim.x * blockDim.x;
+  const uint32_t nv_pad = (nv + 31u) & ~31u;  // whole warps stay in the loop (cooperative part below)
+  for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < nv_pad; j += stride) {
+    uint2 en = make_uint2(0u, kNoRect);
+    if (j < nv) en = __ldg(ent + j);
+    const uint32_t r = en.y;
+    uint32_t bx0 = 0, by0 = 0, w = 0, h = 0, step = 1, n_own = 0;
+    size_t base = 0;
+    float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f);
+    float2 r1 = make_float2(0.f, 0.f);
+    bool multi = false;
+    if (r != kNoRect) {
+      bx0 = r & 255u;
+      by0 = (r >> 16) & 255u;
+      h = (r >> 24) - by0 + 1u;
+      w = ((r >> 8) & 255u) - bx0 + 1u;
+      multi = w * h > 1u;
+      if (rc.shard_world > 1) {  // owned columns of the rectangle: first, first + world, ...
+        owned_span(bx0, (r >> 8) & 255u, rc.shard_rank, rc.shard_world, bx0, w);
+        step = rc.shard_world;
+      }
+      n_own = w * h;
+      base = (size_t)__ldg(slice_prefix + (j >> 8)) + __ldg(ent_off + j);
+      if (multi) {
+        r0 = __ldg(proj_rec + 2 * (size_t)en.x);
+        r1 = __ldg((const float2 *)(proj_rec + 2 * (size_t)en.x + 1));
+      }
+    }
+    const bool big = n_own > 8u;
+    if (!big) {
+      for (uint32_t k = 0; k < n_own; ++k) {
+        const uint32_t row = k / w;
+        emit_candidate(rc, bx0 + (k - row * w) * step, by0 + row, multi, r0, r1, bin_open, en.x, base + k, inst_tile, inst_idx);
+      }
+    }
+    // large rectangles: the warp finishes them together
+    uint32_t todo = __ballot_sync(0xffffffffu, big);
+    while (todo) {
+      const int src = __ffs(todo) - 1;
+      todo &= todo - 1;
+      const uint32_t s_bx0 = __shfl_sync(0xffffffffu, bx0, src), s_by0 = __shfl_sync(0xffffffffu, by0, src);
+      const uint32_t s_w = __shfl_sync(0xffffffffu, w, src), s_step = __shfl_sync(0xffffffffu, step, src);
+      const uint32_t s_n = __shfl_sync(0xffffffffu, n_own, src), s_pay = __shfl_sync(0xffffffffu, en.x, src);
+      const unsigned long long s_base = __shfl_sync(0xffffffffu, (unsigned long long)base, src);
+      float4 g0;
+      float2 g1;
+      g0.x = __shfl_sync(0xffffffffu, r0.x, src); g0.y = __shfl_sync(0xffffffffu, r0.y, src);
+      g0.z = __shfl_sync(0xffffffffu, r0.z, src); g0.w = __shfl_sync(0xffffffffu, r0.w, src);
+      g1.x = __shfl_sync(0xffffffffu, r1.x, src); g1.y = __shfl_sync(0xffffffffu, r1.y, src);
+      for (uint32_t k = lane; k < s_n; k += 32u) {
+        const uint32_t row = k / s_w;
+        emit_candidate(rc, s_bx0 + (k - row * s_w) * s_step, s_by0 + row, true, g0, g1, bin_open, s_pay, (size_t)s_base + k, inst_tile,
+                       inst_idx);
+      }
+    }
+  }
+}
+
 void launch_project(gs_context *c, const FrameParams *fp, const FrameBufs &b, cudaStream_t stream) {
   uint64_t blocks = ((uint64_t)c->cap + 255) / 256;
   const uint64_t cap = (uint64_t)c->sm_count * 16;
@@ -539,6 +629,11 @@ static void launch_emit_impl(gs_context *c, const FrameParams *fp, FrameCounters
   else
     k_count<false><<<(int)tiles, kEmitThreads, 0, st>>>(b.order, b.rect, c->ent, c->ent_off, c->slice_total, c->slice_prefix, ctr, fp,
                                                         nullptr);
+  if (slab) {
+    k_emit_entries<<<(int)tiles, 256, 0, st>>>(c->ent, c->ent_off, c->slice_prefix, b.proj_rec, fp, c->cap_inst, c->inst_tile,
+                                               c->inst_idx, ctr, c->bin_open);
+    return;
+  }
   uint64_t wins = (c->cap_inst + kEmitWindow - 1) / kEmitWindow;
   if (wins > (uint64_t)c->sm_count * 4) wins = (uint64_t)c->sm_count * 4;
   if (wins < 1) wins = 1;

@@ -125,6 +125,8 @@ struct RadixArgs {
   uint32_t t1_final;
   uint2 *bin_range;   // t1_final: the per-bin {start, end} fall out of the digit totals (no k_tile_ranges launch)
   uint32_t n_bins;
+  uint32_t t1_chunk_cols;  // T1's histogram columns: 0 = one per 2048-instance window (produced by k_emit),
+                           // 1 = one per 4096-element chunk (k_radix_hist<T1>, slab path)
 };
 
 template <int PASS>
@@ -227,7 +229,7 @@ __global__ void __launch_bounds__(256) k_radix_scan(RadixArgs a) {
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t n = pass_n<PASS>(a);
   // T1's histograms come from k_emit, one column per 2048-instance window (two per 4096-element chunk)
-  const uint32_t col_elems = (PASS == PASS_T1) ? (uint32_t)kRadixTile / 2 : (uint32_t)kRadixTile;
+  const uint32_t col_elems = (PASS == PASS_T1 && !a.t1_chunk_cols) ? (uint32_t)kRadixTile / 2 : (uint32_t)kRadixTile;
   const uint32_t num_chunks = (n + col_elems - 1) / col_elems;
   uint32_t *row = a.table + (size_t)blockIdx.x * a.stride;
   if (tid == 0) s_carry = 0;
@@ -304,7 +306,7 @@ __global__ void __launch_bounds__(kScatThreads, 2) k_radix_scatter(RadixArgs a) 
 
   for (uint32_t c = blockIdx.x; c < num_chunks; c += gridDim.x) {
     // this chunk's per-digit offset: issued first so its latency hides behind the ranking
-    const uint32_t toff = tid < 256 ? __ldg(a.table + (size_t)tid * a.stride + (PASS == PASS_T1 ? 2 * c : c)) : 0u;
+    const uint32_t toff = tid < 256 ? __ldg(a.table + (size_t)tid * a.stride + ((PASS == PASS_T1 && !a.t1_chunk_cols) ? 2 * c : c)) : 0u;
     for (uint32_t k = tid; k < kScatWarps * 256; k += kScatThreads) (&wcnt[0][0])[k] = 0u;
     // ---- load (warp-striped: consecutive lanes read consecutive elements) ----
     const uint32_t base = c * kRadixTile + warp * (32 * kScatItems) + lane;
@@ -464,14 +466,16 @@ void launch_tile_ranges(gs_context *c, FrameCounters *ctr, const FrameBufs &b, c
 
 // stable sort of the tile instances by tile id (5 launches: T1's histogram is produced by k_emit);
 // T2 writes the per-tile record lists
-void launch_tile_radix(gs_context *c, FrameCounters *ctr, const FrameBufs &b, uint32_t n_bins, cudaStream_t st) {
+void launch_tile_radix(gs_context *c, FrameCounters *ctr, const FrameBufs &b, uint32_t n_bins, bool hist_t1, cudaStream_t st) {
   RadixArgs a = make_args(c, nullptr, ctr, b);
+  a.t1_chunk_cols = hist_t1 ? 1u : 0u;
   a.table = c->table_d;
   a.totals = c->totals + 256;
   a.stride = c->table_d_stride;
   a.t1_final = n_bins <= 256u ? 1u : 0u;  // one byte of bin id: T1 alone sorts, gathers the records and writes the ranges
   a.bin_range = b.bin_range;
   a.n_bins = n_bins;
+  if (hist_t1) k_radix_hist<PASS_T1><<<persistent_grid(c, c->cap_inst, kRadixTile, 8), kRadixThreads, 0, st>>>(a);
   run_pass<PASS_T1>(c, a, c->cap_inst, st);
   if (!a.t1_final) {
     run_pass<PASS_T2>(c, a, c->cap_inst, st);
