@@ -266,6 +266,7 @@ extern "C" int gs_create(int device_ordinal, gs_context **out_ctx) {
   c->use_graphs = getenv("GS_NO_GRAPH") == nullptr;
   // frames expected to sort at least GS_SLAB_MIN splats (default 16 M) are rendered front to back in depth slabs (gs_slab.cu);
   // GS_SLAB_FIRST = target entry count of the nearest slab (default 1 M, the following ones double)
+  if (const char *e = getenv("GS_EMIT")) c->emit_by_entry = strcmp(e, "entries") == 0;
   if (const char *e = getenv("GS_SLAB_MIN")) c->slab_min = (uint32_t)strtoull(e, nullptr, 10);
   if (const char *e = getenv("GS_SLAB_FIRST")) c->slab_first = std::max<uint32_t>(1024u, (uint32_t)strtoull(e, nullptr, 10));
   {  // pixel loop of the raster: packed fp32x2 (default) or scalar (GS_RASTER=scalar); both give identical frames
@@ -585,7 +586,7 @@ static cudaError_t enqueue_bin_stage(gs_context *c, gs_context::Slot &sl, uint32
   if ((e = cudaMemsetAsync(b.bin_range, 0, sizeof(uint2) * (size_t)n_bins, m))) return e;
   if ((e = rec(sl.ev[2], m))) return e;
   launch_emit(c, sl.fp, sl.ctr, b, m);   // 2 launches (k_emit also histograms pass T1)
-  launch_tile_radix(c, sl.ctr, b, n_bins, false, m);    // 2 launches (<= 256 bins) or 6 (incl. k_tile_ranges)
+  launch_tile_radix(c, sl.ctr, b, n_bins, c->emit_by_entry, m);    // 2 launches (<= 256 bins) or 6 (incl. k_tile_ranges)
   if ((e = rec(sl.ev[3], m))) return e;
   return cudaGetLastError();
 }

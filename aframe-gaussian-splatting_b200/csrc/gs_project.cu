@@ -629,9 +629,9 @@ static void launch_emit_impl(gs_context *c, const FrameParams *fp, FrameCounters
   else
     k_count<false><<<(int)tiles, kEmitThreads, 0, st>>>(b.order, b.rect, c->ent, c->ent_off, c->slice_total, c->slice_prefix, ctr, fp,
                                                         nullptr);
-  if (slab) {
+  if (slab || c->emit_by_entry) {
     k_emit_entries<<<(int)tiles, 256, 0, st>>>(c->ent, c->ent_off, c->slice_prefix, b.proj_rec, fp, c->cap_inst, c->inst_tile,
-                                               c->inst_idx, ctr, c->bin_open);
+                                               c->inst_idx, ctr, slab ? c->bin_open : nullptr);
     return;
   }
   uint64_t wins = (c->cap_inst + kEmitWindow - 1) / kEmitWindow;
