@@ -266,7 +266,7 @@ extern "C" int gs_create(int device_ordinal, gs_context **out_ctx) {
   c->use_graphs = getenv("GS_NO_GRAPH") == nullptr;
   // frames expected to sort at least GS_SLAB_MIN splats (default 16 M) are rendered front to back in depth slabs (gs_slab.cu);
   // GS_SLAB_FIRST = target entry count of the nearest slab (default 1 M, the following ones double)
-  if (const char *e = getenv("GS_EMIT")) c->emit_by_entry = strcmp(e, "entries") == 0;
+  if (const char *e = getenv("GS_EMIT")) c->emit_by_entry = strcmp(e, "windows") != 0;
   if (const char *e = getenv("GS_SLAB_MIN")) c->slab_min = (uint32_t)strtoull(e, nullptr, 10);
   if (const char *e = getenv("GS_SLAB_FIRST")) c->slab_first = std::max<uint32_t>(1024u, (uint32_t)strtoull(e, nullptr, 10));
   {  // pixel loop of the raster: packed fp32x2 (default) or scalar (GS_RASTER=scalar); both give identical frames
@@ -664,7 +664,7 @@ static int launch_frame(gs_context *c, gs_context::Slot &sl, bool reuse, uint32_
     // depth-tested / statistics frames use other instantiations of the raster: plain launches, no cached graph
     GS_CUDA(c, enqueue_raster_stage(c, sl, n_tiles, false));
   }
-  sl.launches = (reuse ? 0u : 7u) + 1u + (n_bins <= 256u ? 4u : 8u) + 1u;
+  sl.launches = (reuse ? 0u : 7u) + 1u + (n_bins <= 256u ? 4u : 8u) + (c->emit_by_entry ? 1u : 0u) + 1u;
   return GS_OK;
 }
 

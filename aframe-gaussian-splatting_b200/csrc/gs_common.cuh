@@ -189,7 +189,8 @@ struct gs_context {
   bool have_last_sorted = false;
   uint32_t slab_first = 1u << 20;  // target entry count of the nearest slab (the following ones double)
   int last_mode = 0;               // 0 = one pass (three-stage pipeline), 1 = slab path
-  bool emit_by_entry = false;      // one-pass path: k_emit_entries + k_radix_hist<T1> instead of the window-balanced k_emit (GS_EMIT=entries)
+  bool emit_by_entry = true;       // k_emit_entries + k_radix_hist<T1> (default; measured faster on every config) or, with
+                                   // GS_EMIT=windows, the window-balanced k_emit of round 1 (one-pass path only)
   uint4 *tile_stats = nullptr;     // [tiles] per-tile counts of a GS_RENDER_STATS frame
   uint4 *tile_stats_host = nullptr;  // pinned copy
   uint32_t tile_stats_cap = 0;
