@@ -22,7 +22,8 @@
 //   k_raster  <.., false>: 256 threads, one pixel per lane, scalar fp32;
 //   k_raster  <.., true> : 128 threads, two vertically adjacent pixels per lane, packed fp32x2 arithmetic
 //                          (FADD2 / FMUL2 / FFMA2: one issue slot per two lane-operations; the kernel is bound by
-//                          issue slots, not by the fp32 pipe itself).
+//                          issue slots, not by the fp32 pipe itself).  The per-splat operands stay scalars in shared
+//                          memory: the packed instructions broadcast a scalar register operand (`Rn.F32`) themselves.
 #include "gs_common.cuh"
 
 namespace gs {
@@ -124,7 +125,7 @@ struct RasterCfg {
   static constexpr int kThreads = PACKED ? 128 : 256;
   static constexpr int kChunk = PACKED ? 128 : 256;   // records per TMA bulk copy == one cull pass (one record per thread)
   static constexpr int kStages = PACKED ? GS_RASTER_STAGES : 3;  // ring depth
-  static constexpr int kCv = PACKED ? 5 : 3;           // float4 per converted record
+  static constexpr int kCv = 3;                        // float4 per converted record
   static constexpr int kMinBlocks = PACKED ? GS_RASTER_MINB : 4;
 };
 
@@ -267,11 +268,9 @@ __global__ void __launch_bounds__(RasterCfg<PACKED>::kThreads, RasterCfg<PACKED>
       const float zw = __fadd_rn(__fmul_rn(r1.w, 0.5f), 0.5f);
       float4 *cv = &s_cv[pos * kCv];
       if (PACKED) {
-        cv[0] = make_float4(-r0.x, r1.x, r0.z, zw);     // -cx, a2x, a1x, zw
-        cv[1] = make_float4(-r0.y, -r0.y, r1.y, r1.y);  // (-cy, -cy), (a2y, a2y)
-        cv[2] = make_float4(r0.w, r0.w, ca, ca);        // (a1y, a1y), (alpha, alpha)
-        cv[3] = make_float4(cr, cr, cg, cg);
-        cv[4] = make_float4(cb, cb, 0.f, 0.f);
+        cv[0] = make_float4(-r0.x, r1.x, r0.z, zw);   // -cx, a2x, a1x, zw
+        cv[1] = make_float4(-r0.y, r1.y, r0.w, ca);   // -cy, a2y, a1y, alpha
+        cv[2] = make_float4(cr, cg, cb, 0.f);
       } else {
         cv[0] = r0;
         cv[1] = make_float4(r1.x, r1.y, zw, ca);
@@ -285,14 +284,14 @@ __global__ void __launch_bounds__(RasterCfg<PACKED>::kThreads, RasterCfg<PACKED>
       if (lim0 > 0.0f || lim1 > 0.0f) {
 #pragma unroll 2
         for (int j = (int)kept - 1; j >= 0; --j) {
-          const float4 q0 = s_cv[j * kCv], q1 = s_cv[j * kCv + 1], q2 = s_cv[j * kCv + 2];
+          const float4 q0 = s_cv[j * kCv], q1 = s_cv[j * kCv + 1];
           // vPosition = (px, py) with the op order of the oracle (orc band_worker): d = sample - centre,
           // px = fma(dy, a2y, dx*a2x), py = fma(dy, a1y, dx*a1x), r2 = fma(py, py, px*px)
           const float dx = __fadd_rn(fx, q0.x);
-          const float2 dy2 = __fadd2_rn(fy2, make_float2(q1.x, q1.y));
+          const float2 dy2 = __fadd2_rn(fy2, make_float2(q1.x, q1.x));
           const float t = __fmul_rn(dx, q0.y), u = __fmul_rn(dx, q0.z);
-          const float2 px2 = __ffma2_rn(dy2, make_float2(q1.z, q1.w), make_float2(t, t));
-          const float2 py2 = __ffma2_rn(dy2, make_float2(q2.x, q2.y), make_float2(u, u));
+          const float2 px2 = __ffma2_rn(dy2, make_float2(q1.y, q1.y), make_float2(t, t));
+          const float2 py2 = __ffma2_rn(dy2, make_float2(q1.z, q1.z), make_float2(u, u));
           const float2 r22 = __ffma2_rn(py2, py2, __fmul2_rn(px2, px2));
           bool h0 = r22.x <= lim0, h1 = r22.y <= lim1;  // index.js:171-172: A = -r2; discard if A < -4
           if (DEPTH) { h0 = h0 && (q0.w <= d0); h1 = h1 && (q0.w <= d1); }
@@ -300,15 +299,14 @@ __global__ void __launch_bounds__(RasterCfg<PACKED>::kThreads, RasterCfg<PACKED>
           if (h0 || h1) {
             const float2 m2 = __fmul2_rn(r22, make_float2(kNegLog2e, kNegLog2e));
             const float2 e2 = make_float2(ex2_approx(m2.x), ex2_approx(m2.y));
-            const float2 al2 = __fmul2_rn(e2, make_float2(q2.z, q2.w));  // index.js:173
+            const float2 al2 = __fmul2_rn(e2, make_float2(q1.w, q1.w));  // index.js:173
             float2 w2 = __fmul2_rn(al2, T2);
             w2.x = h0 ? w2.x : 0.0f;
             w2.y = h1 ? w2.y : 0.0f;
-            const float4 q3 = s_cv[j * kCv + 3];
-            const float2 q4 = *(const float2 *)&s_cv[j * kCv + 4];
-            R2 = __ffma2_rn(make_float2(q3.x, q3.y), w2, R2);
-            G2 = __ffma2_rn(make_float2(q3.z, q3.w), w2, G2);
-            B2 = __ffma2_rn(q4, w2, B2);
+            const float4 q2 = s_cv[j * kCv + 2];
+            R2 = __ffma2_rn(make_float2(q2.x, q2.x), w2, R2);
+            G2 = __ffma2_rn(make_float2(q2.y, q2.y), w2, G2);
+            B2 = __ffma2_rn(make_float2(q2.z, q2.z), w2, B2);
             T2 = __ffma2_rn(w2, make_float2(-1.0f, -1.0f), T2);  // T - w, one rounding
             lim0 = (T2.x >= kTStop) ? lim0 : -1.0f;
             lim1 = (T2.y >= kTStop) ? lim1 : -1.0f;
