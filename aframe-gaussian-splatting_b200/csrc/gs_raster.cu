@@ -114,6 +114,10 @@ __device__ __forceinline__ void store_pixel(const FrameParams *fp, uint32_t tile
   }
 }
 
+#ifndef GS_RASTER_UNROLL
+#define GS_RASTER_UNROLL 2   // records per iteration of the packed pixel loop
+#endif
+constexpr int kPackedUnroll = GS_RASTER_UNROLL;
 #ifndef GS_RASTER_STAGES
 #define GS_RASTER_STAGES 4   // TMA ring depth of the packed kernel
 #endif
@@ -282,7 +286,7 @@ __global__ void __launch_bounds__(RasterCfg<PACKED>::kThreads, RasterCfg<PACKED>
     // ---- 2. composite the kept records, nearest first ----
     if (PACKED) {
       if (lim0 > 0.0f || lim1 > 0.0f) {
-#pragma unroll 2
+#pragma unroll kPackedUnroll
         for (int j = (int)kept - 1; j >= 0; --j) {
           const float4 q0 = s_cv[j * kCv], q1 = s_cv[j * kCv + 1];
           // vPosition = (px, py) with the op order of the oracle (orc band_worker): d = sample - centre,
