@@ -261,6 +261,7 @@ struct gs_context {
   cudaStream_t aux_stream = nullptr;             // runs k_project beside the depth radix passes
   cudaEvent_t ev_fork[2]{}, ev_join[2]{};
   bool use_graphs = true;
+  bool use_pdl = true;                           // programmatic dependent launch inside the stage chains (GS_PDL=0 turns it off)
   uint32_t raster_base_flags = 1;                // default pixel loop: 1 = packed fp32x2, 0 = scalar
   // graph cache key: anything baked into the captured launches
   struct GraphKey { uint32_t cap = 0, n_tiles = 0, n_bins = 0, pad = 0; uint64_t cap_inst = 0; const void *p0 = nullptr, *p1 = nullptr, *p2 = nullptr; } gkey;
@@ -324,6 +325,29 @@ void launch_raster_slab(gs_context *c, const FrameParams *fp, FrameCounters *ctr
 void launch_resolve(gs_context *c, const FrameParams *fp, uint32_t n_tiles, cudaStream_t st);
 void launch_assemble(gs_context *c, const void *gathered, uint32_t tiles_per_rank, uint32_t world, uint32_t width,
                      uint32_t height, int32_t format, void *out_frame);
+
+// ---- programmatic dependent launch (PDL): the kernels of a stage form a chain of short dependent launches.  Launched
+// with the programmatic-stream-serialization attribute, kernel k+1 is set up (CTAs scheduled, arguments loaded) while
+// kernel k drains; it blocks in pdl_wait() until k has completed and its writes are visible.  Every kernel launched
+// this way calls pdl_trigger() + pdl_wait() before its first global access.  GS_PDL=0 disables it. ----
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#define GS_PDL_ENTRY() do { gs::pdl_trigger(); gs::pdl_wait(); } while (0)
+
+template <class... KArgs, class... Args>
+inline cudaError_t launch_chain(gs_context *c, void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t st, Args &&...args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+  cudaLaunchAttribute attr{};
+  attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr.val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = &attr;
+  cfg.numAttrs = c->use_pdl ? 1u : 0u;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
 
 // order-preserving u64 encoding of an fp64 value (for atomicMin / atomicMax)
 __host__ __device__ inline unsigned long long enc_f64(double d) {

@@ -42,6 +42,7 @@ __global__ void __launch_bounds__(256) k_project(const float4 *__restrict__ cs, 
                                                  const FrameParams *__restrict__ fp, float4 *__restrict__ rec_out,
                                                  uint32_t *__restrict__ rect_out, const uint32_t *__restrict__ order,
                                                  const FrameCounters *__restrict__ ctr) {
+  GS_PDL_ENTRY();
   const RenderConsts &rc = fp->rc;
   const uint32_t n = BY_ENTRY ? ctr->sort.n_valid : fp->n_splats;
   const uint32_t stride = gridDim.x * blockDim.x;
@@ -180,6 +181,7 @@ __global__ void __launch_bounds__(kEmitThreads) k_count(const uint32_t *__restri
                                                         uint32_t *__restrict__ slice_prefix, FrameCounters *ctr,
                                                         const FrameParams *__restrict__ fp,
                                                         const uint32_t *__restrict__ bin_open) {
+  GS_PDL_ENTRY();
   const uint32_t shard_rank = fp->rc.shard_rank, shard_world = fp->rc.shard_world;
   __shared__ uint32_t s_warp[kEmitThreads / 32], s_vis[kEmitThreads / 32];
   __shared__ uint32_t s_last;
@@ -302,6 +304,7 @@ __global__ void __launch_bounds__(kEmitThreads, 4) k_emit(const uint2 *__restric
                                                           uint16_t *__restrict__ inst_tile, uint32_t *__restrict__ inst_idx,
                                                           uint32_t *__restrict__ table_t1, uint32_t table_stride,
                                                           FrameCounters *ctr, const uint32_t *__restrict__ bin_open) {
+  GS_PDL_ENTRY();
   const RenderConsts &rc = fp->rc;
   __shared__ uint32_t s_wi[kEmitThreads * (kEmitPerThread + 1)];  // stride 9: conflict-free staging
   __shared__ uint16_t s_wt[kEmitThreads * (kEmitPerThread + 1)];
@@ -530,6 +533,7 @@ __global__ void __launch_bounds__(256) k_emit_entries(const uint2 *__restrict__ 
                                                       uint64_t cap_inst, uint16_t *__restrict__ inst_tile,
                                                       uint32_t *__restrict__ inst_idx, FrameCounters *ctr,
                                                       const uint32_t *__restrict__ bin_open) {
+  GS_PDL_ENTRY();
   const RenderConsts &rc = fp->rc;
   const uint32_t nv = ctr->sort.n_valid;
   if (ctr->n_inst > cap_inst) {  // instance buffer too small: the host regrows it and re-runs the frame
@@ -600,7 +604,8 @@ void launch_project(gs_context *c, const FrameParams *fp, const FrameBufs &b, cu
   const uint64_t cap = (uint64_t)c->sm_count * 16;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
-  k_project<false><<<(int)blocks, 256, 0, stream>>>(c->center_scale, c->cov_color, c->depth, fp, b.proj_rec, b.rect, nullptr, nullptr);
+  launch_chain(c, k_project<false>, (int)blocks, 256, stream, (const float4 *)c->center_scale, (const uint4 *)c->cov_color, (const float *)c->depth, fp, b.proj_rec, b.rect,
+               (const uint32_t *)nullptr, (const FrameCounters *)nullptr);
 }
 
 void launch_project_entries(gs_context *c, const FrameParams *fp, FrameCounters *ctr, const FrameBufs &b, cudaStream_t stream) {
@@ -608,7 +613,8 @@ void launch_project_entries(gs_context *c, const FrameParams *fp, FrameCounters 
   const uint64_t cap = (uint64_t)c->sm_count * 16;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
-  k_project<true><<<(int)blocks, 256, 0, stream>>>(c->center_scale, c->cov_color, c->depth, fp, b.proj_rec, b.rect, b.order, ctr);
+  launch_chain(c, k_project<true>, (int)blocks, 256, stream, (const float4 *)c->center_scale, (const uint4 *)c->cov_color, (const float *)c->depth, fp, b.proj_rec, b.rect,
+               (const uint32_t *)b.order, (const FrameCounters *)ctr);
 }
 
 static void launch_emit_impl(gs_context *c, const FrameParams *fp, FrameCounters *ctr, const FrameBufs &b, cudaStream_t st, bool slab);
@@ -624,14 +630,15 @@ static void launch_emit_impl(gs_context *c, const FrameParams *fp, FrameCounters
   if (tiles > cap) tiles = cap;
   if (tiles < 1) tiles = 1;
   if (slab)
-    k_count<true><<<(int)tiles, kEmitThreads, 0, st>>>(b.order, b.rect, c->ent, c->ent_off, c->slice_total, c->slice_prefix, ctr, fp,
-                                                       c->bin_open);
+    launch_chain(c, k_count<true>, (int)tiles, kEmitThreads, st, (const uint32_t *)b.order, (const uint32_t *)b.rect, c->ent, c->ent_off,
+                 c->slice_total, c->slice_prefix, ctr, fp, (const uint32_t *)c->bin_open);
   else
-    k_count<false><<<(int)tiles, kEmitThreads, 0, st>>>(b.order, b.rect, c->ent, c->ent_off, c->slice_total, c->slice_prefix, ctr, fp,
-                                                        nullptr);
+    launch_chain(c, k_count<false>, (int)tiles, kEmitThreads, st, (const uint32_t *)b.order, (const uint32_t *)b.rect, c->ent, c->ent_off,
+                 c->slice_total, c->slice_prefix, ctr, fp, (const uint32_t *)nullptr);
   if (slab || c->emit_by_entry) {
-    k_emit_entries<<<(int)tiles, 256, 0, st>>>(c->ent, c->ent_off, c->slice_prefix, b.proj_rec, fp, c->cap_inst, c->inst_tile,
-                                               c->inst_idx, ctr, slab ? c->bin_open : nullptr);
+    launch_chain(c, k_emit_entries, (int)tiles, 256, st, (const uint2 *)c->ent, (const uint32_t *)c->ent_off, (const uint32_t *)c->slice_prefix,
+                 (const float4 *)b.proj_rec, fp, (uint64_t)c->cap_inst, c->inst_tile, c->inst_idx, ctr,
+                 (const uint32_t *)(slab ? c->bin_open : nullptr));
     return;
   }
   uint64_t wins = (c->cap_inst + kEmitWindow - 1) / kEmitWindow;

@@ -23,6 +23,7 @@ namespace gs {
 __global__ void __launch_bounds__(256) k_depth_cull(const float4 *__restrict__ cs, const float *__restrict__ sa,
                                                     const FrameParams *__restrict__ fp,
                                                     float *__restrict__ depth_out, FrameCounters *ctr) {
+  GS_PDL_ENTRY();
   const SortConsts sc = fp->sc;
   const uint32_t n = fp->n_splats;  // resident splats when the frame was submitted (a push may be appending more)
   double dmin = INFINITY, dmax = -INFINITY;
@@ -174,6 +175,7 @@ __device__ __forceinline__ void load_elem(const RadixArgs &a, uint32_t i, const 
 
 template <int PASS>
 __global__ void __launch_bounds__(kRadixThreads) k_radix_hist(RadixArgs a) {
+  GS_PDL_ENTRY();
   __shared__ uint32_t h[256];
   __shared__ uint32_t s_in, s_drop;
   FrameCounters *ctr = a.ctr;
@@ -224,6 +226,7 @@ __global__ void __launch_bounds__(kRadixThreads) k_radix_hist(RadixArgs a) {
 // grid = 256 CTAs (one per digit)
 template <int PASS>
 __global__ void __launch_bounds__(256) k_radix_scan(RadixArgs a) {
+  GS_PDL_ENTRY();
   __shared__ uint32_t s_warp[8];
   __shared__ uint32_t s_carry;
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -266,6 +269,7 @@ constexpr int kScatWarps = kScatThreads / 32;          // 16
 
 template <int PASS>
 __global__ void __launch_bounds__(kScatThreads, 2) k_radix_scatter(RadixArgs a) {
+  GS_PDL_ENTRY();
   __shared__ uint32_t wcnt[kScatWarps][256];
   __shared__ uint32_t tile_off[256];  // global slot of the digit's first element MINUS its slot in the staged chunk
   __shared__ uint32_t s_loc[256];     // slot of the digit's first element in the staged (locally sorted) chunk
@@ -404,6 +408,7 @@ __global__ void __launch_bounds__(kScatThreads, 2) k_radix_scatter(RadixArgs a) 
 // the {0, 0} the per-frame memset wrote.  One thread per instance, neighbours compared.
 __global__ void __launch_bounds__(256) k_tile_ranges(const uint16_t *__restrict__ tile_f, FrameCounters *ctr,
                                                      uint2 *__restrict__ range) {
+  GS_PDL_ENTRY();
   const uint32_t n = ctr->overflow ? 0u : ctr->n_inst_kept;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const uint32_t t = tile_f[i];
@@ -423,7 +428,7 @@ void launch_depth_cull(gs_context *c, const FrameParams *fp, FrameCounters *ctr,
   // grids are sized by the table CAPACITY (stable across pushes) and the kernels read the splat count from fp, so a
   // captured frame graph stays valid while a scene is still loading
   const int grid = persistent_grid(c, c->cap, 256 * 4, 8);
-  k_depth_cull<<<grid, 256, 0, st>>>(c->center_scale, c->size_alpha, fp, c->depth, ctr);
+  launch_chain(c, k_depth_cull, grid, 256, st, c->center_scale, c->size_alpha, fp, c->depth, ctr);
 }
 
 static RadixArgs make_args(gs_context *c, const FrameParams *fp, FrameCounters *ctr, const FrameBufs &b) {
@@ -447,9 +452,9 @@ static RadixArgs make_args(gs_context *c, const FrameParams *fp, FrameCounters *
 template <int PASS>
 static void run_pass(gs_context *c, RadixArgs &a, uint64_t n_max, cudaStream_t st) {
   const int grid = persistent_grid(c, n_max, kRadixTile, 8);
-  if (PASS != PASS_T1) k_radix_hist<PASS><<<grid, kRadixThreads, 0, st>>>(a);
-  k_radix_scan<PASS><<<256, 256, 0, st>>>(a);
-  k_radix_scatter<PASS><<<grid, kScatThreads, 0, st>>>(a);
+  if (PASS != PASS_T1) launch_chain(c, k_radix_hist<PASS>, grid, kRadixThreads, st, a);
+  launch_chain(c, k_radix_scan<PASS>, 256, 256, st, a);
+  launch_chain(c, k_radix_scatter<PASS>, grid, kScatThreads, st, a);
 }
 
 // index.js:557-567 as two stable 8-bit passes -> b.order (6 launches)
@@ -475,7 +480,7 @@ void launch_tile_radix(gs_context *c, FrameCounters *ctr, const FrameBufs &b, ui
   a.t1_final = n_bins <= 256u ? 1u : 0u;  // one byte of bin id: T1 alone sorts, gathers the records and writes the ranges
   a.bin_range = b.bin_range;
   a.n_bins = n_bins;
-  if (hist_t1) k_radix_hist<PASS_T1><<<persistent_grid(c, c->cap_inst, kRadixTile, 8), kRadixThreads, 0, st>>>(a);
+  if (hist_t1) launch_chain(c, k_radix_hist<PASS_T1>, persistent_grid(c, c->cap_inst, kRadixTile, 8), kRadixThreads, st, a);
   run_pass<PASS_T1>(c, a, c->cap_inst, st);
   if (!a.t1_final) {
     run_pass<PASS_T2>(c, a, c->cap_inst, st);
@@ -492,15 +497,15 @@ void launch_slab_sort(gs_context *c, const FrameParams *fp, FrameCounters *ctr, 
   a.ckey = c->ckey;
   a.cidx = c->cidx;
   const int grid = persistent_grid(c, c->cap, kRadixTile, 8);
-  k_radix_hist<PASS_S1><<<grid, kRadixThreads, 0, st>>>(a);
-  k_radix_scan<PASS_S1><<<256, 256, 0, st>>>(a);
-  k_radix_scatter<PASS_S1><<<grid, kScatThreads, 0, st>>>(a);
+  launch_chain(c, k_radix_hist<PASS_S1>, grid, kRadixThreads, st, a);
+  launch_chain(c, k_radix_scan<PASS_S1>, 256, 256, st, a);
+  launch_chain(c, k_radix_scatter<PASS_S1>, grid, kScatThreads, st, a);
   run_pass<PASS_D2>(c, a, c->cap, st);
 }
 
 void launch_tile_ranges(gs_context *c, FrameCounters *ctr, const FrameBufs &b, cudaStream_t st) {
   const int grid = persistent_grid(c, c->cap_inst, 256 * 8, 8);
-  k_tile_ranges<<<grid, 256, 0, st>>>(c->inst_tile_f, ctr, b.bin_range);
+  launch_chain(c, k_tile_ranges, grid, 256, st, (const uint16_t *)c->inst_tile_f, ctr, b.bin_range);
 }
 
 }  // namespace gs
