@@ -266,7 +266,7 @@ extern "C" int gs_create(int device_ordinal, gs_context **out_ctx) {
   c->use_graphs = getenv("GS_NO_GRAPH") == nullptr;
   // frames expected to sort at least GS_SLAB_MIN splats (default 16 M) are rendered front to back in depth slabs (gs_slab.cu);
   // GS_SLAB_FIRST = target entry count of the nearest slab (default 1 M, the following ones double)
-  if (const char *e = getenv("GS_PDL")) c->use_pdl = strcmp(e, "0") != 0;
+  if (const char *e = getenv("GS_PDL")) c->use_pdl = strcmp(e, "1") == 0;
   if (const char *e = getenv("GS_EMIT")) c->emit_by_entry = strcmp(e, "windows") != 0;
   if (const char *e = getenv("GS_SLAB_MIN")) c->slab_min = (uint32_t)strtoull(e, nullptr, 10);
   if (const char *e = getenv("GS_SLAB_FIRST")) c->slab_first = std::max<uint32_t>(1024u, (uint32_t)strtoull(e, nullptr, 10));
