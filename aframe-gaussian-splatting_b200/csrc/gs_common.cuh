@@ -30,7 +30,10 @@ constexpr int kTile = 16;                 // 16x16 screen tiles (north_star): on
 constexpr int kTilesPerBin = GS_BIN_TILES;  // tile columns / rows per bin
 constexpr int kBin = kTile * kTilesPerBin;  // bin edge in pixels (96 by default; gs_bin_size() reports it)
 constexpr int kRadixThreads = 256;
-constexpr int kRadixItems = 16;
+#ifndef GS_RADIX_ITEMS
+#define GS_RADIX_ITEMS 16
+#endif
+constexpr int kRadixItems = GS_RADIX_ITEMS;  // elements per thread of a radix chunk (chunk = 256 x this)
 constexpr int kRadixTile = kRadixThreads * kRadixItems;  // 4096 elements per radix chunk
 constexpr int kEmitThreads = 256;
 constexpr int kEmitItems = 1;

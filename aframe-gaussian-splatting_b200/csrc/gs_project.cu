@@ -152,7 +152,7 @@ __global__ void __launch_bounds__(256) k_project(const float4 *__restrict__ cs, 
 }
 
 
-constexpr int kEmitPerThread = 8;
+constexpr int kEmitPerThread = kRadixTile / 2 / kEmitThreads;  // 8: one emission window = half a radix chunk
 constexpr int kEmitWindow = kEmitThreads * kEmitPerThread;  // 2048 instances per CTA iteration
 
 // candidate tiles of a packed rectangle that this rank owns (all of them on one GPU)
