@@ -231,6 +231,10 @@ extern "C" int gs_create(int device_ordinal, gs_context **out_ctx) {
   // main / aux streams priority lets their CTAs slot in as raster CTAs retire, so frame k+1 is binned UNDER frame k's raster
   int prio_least = 0, prio_greatest = 0;
   cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest);
+  if (const char *e = getenv("GS_PRIO")) {  // experiment knob: flat = every stage at one priority, inverse = raster first
+    if (strcmp(e, "flat") == 0) prio_greatest = prio_least;
+    if (strcmp(e, "inverse") == 0) std::swap(prio_least, prio_greatest);
+  }
   if ((e = cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio_greatest)) != cudaSuccess) return bail("cudaStreamCreate", e);
   if ((e = cudaStreamCreateWithPriority(&c->bstream, cudaStreamNonBlocking, prio_greatest)) != cudaSuccess) return bail("cudaStreamCreate", e);
   if ((e = cudaStreamCreateWithPriority(&c->rstream, cudaStreamNonBlocking, prio_least)) != cudaSuccess) return bail("cudaStreamCreate", e);
