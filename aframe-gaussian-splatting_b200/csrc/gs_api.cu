@@ -591,7 +591,7 @@ static cudaError_t enqueue_bin_stage(gs_context *c, gs_context::Slot &sl, uint32
   if ((e = cudaMemsetAsync(b.bin_range, 0, sizeof(uint2) * (size_t)n_bins, m))) return e;
   if ((e = rec(sl.ev[2], m))) return e;
   launch_emit(c, sl.fp, sl.ctr, b, m);   // 2 launches (k_emit also histograms pass T1)
-  launch_tile_radix(c, sl.ctr, b, n_bins, c->emit_by_entry, m);    // 2 launches (<= 256 bins) or 6 (incl. k_tile_ranges)
+  launch_tile_radix(c, sl.ctr, b, n_bins, c->emit_by_entry, m);    // (hist +) scan + scatter; above 256 bins also pass T2 + k_tile_ranges
   if ((e = rec(sl.ev[3], m))) return e;
   return cudaGetLastError();
 }
@@ -654,7 +654,7 @@ static int launch_frame(gs_context *c, gs_context::Slot &sl, bool reuse, uint32_
   int rc = run_graph(c, sl.graph_a[set][reuse ? 1 : 0], c->stream, [&](bool ext) { return enqueue_sort_stage(c, sl, reuse, ext); });
   if (rc) return rc;
   GS_CUDA(c, cudaEventRecord(sl.ev_sorted, c->stream));
-  // B: needs A of this frame; inst_rec/tile_range[set] must no longer be read by the raster that used them last
+  // B: needs A of this frame; inst_rec/bin_range[set] must no longer be read by the raster that used them last
   GS_CUDA(c, cudaStreamWaitEvent(c->bstream, sl.ev_sorted, 0));
   if (c->bin_set_free[set]) GS_CUDA(c, cudaStreamWaitEvent(c->bstream, c->bin_set_free[set], 0));
   if ((rc = run_graph(c, sl.graph_b[set], c->bstream, [&](bool ext) { return enqueue_bin_stage(c, sl, n_bins, ext); }))) return rc;

@@ -201,7 +201,7 @@ struct gs_context {
   int quirk_n = 0;
   gs::SortHeader *sort_hdr = nullptr;  // device: counters header of the last sort (for GS_RENDER_REUSE_SORT)
 
-  // ---- two pipeline slots: frame k+1 is rasterised while frame k is copied to the host ----
+  // ---- three pipeline slots (ticket % 3): frame k is rasterised while k+1 is binned, k+2 sorted and k-1 copied to the host ----
   struct Slot {
     gs::FrameCounters *ctr = nullptr;        // device
     gs::FrameCounters *ctr_host = nullptr;   // pinned
@@ -242,12 +242,12 @@ struct gs_context {
     size_t out_bytes = 0;
     gs_render_params params{};
     uint32_t launches = 0;
-    int set = 0;                                    // which order/proj_rec/rect and inst_rec/tile_range copy it uses
+    int set = 0;                                    // which order/proj_rec/rect and inst_rec/bin_range copy it uses
   } slot[3];
   uint64_t next_ticket = 0;
   cudaStream_t bstream = nullptr;                   // binning stage (high priority, like the sort stage's `stream`)
   cudaEvent_t sort_set_free[2] = {nullptr, nullptr};  // last binning stage that read order/proj_rec/rect[i]
-  cudaEvent_t bin_set_free[2] = {nullptr, nullptr};   // last raster that read inst_rec/tile_range[i]
+  cudaEvent_t bin_set_free[2] = {nullptr, nullptr};   // last raster that read inst_rec/bin_range[i]
   int last_set = 0;                                 // set holding the most recent sort (GS_RENDER_REUSE_SORT, read-backs)
   cudaStream_t rstream = nullptr;   // raster stream: frame k is rasterised here while frame k+1 is sorted / binned
   cudaStream_t copy_stream = nullptr;

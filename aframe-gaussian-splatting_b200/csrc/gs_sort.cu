@@ -6,7 +6,7 @@
 //                   counting sort as two 8-bit passes
 //   k_radix_{scan,scatter}<T1>, k_radix_{hist,scan,scatter}<T2>: stable sort of tile instances by 16-bit tile id
 //                   (T1's histograms come from k_emit; T2 also gathers the 32 B records)
-//   k_tile_ranges : per-tile {start, end} in the final instance order
+//   k_tile_ranges : per-bin {start, end} in the final instance order (frames of more than 256 bins; otherwise pass T1 writes them)
 //
 // Bit-exactness: JS evaluates in fp64 with IEEE rounding after every operation; the kernels use
 // __dmul_rn/__dadd_rn so nothing is contracted, and ToInt32 is restated exactly (js_to_int32).

@@ -8,7 +8,9 @@ A "step" is one full frame of the workload: the worker sort request plus the ins
 (reference index.js:438-455 + 184-207), synchronously with the same camera.
 N = 1 workload = BASELINE.json configs[1]: train-like 1 M synthetic splats, 1920x1080, fixed camera; the same run
 then also times configs[2] (6 M, orbit) and configs[3] (20 M, 3840x2160, cutout) and prints them under
-`other_configs`.  N > 1: the same scene, the FRAME sharded by screen tile over the ranks -> strong scaling.
+`other_configs`.  N > 1 (see parallel_mode): by default every rank renders every N-th frame of the stream from its own
+replica of the scene (weak scaling, no data-path collective); `--parallel tiles` (default for the 80 M scene) shards ONE
+frame by screen bin columns over the ranks and exchanges the finished tiles (strong scaling).
 
 `value`  : frames/s with the scene resident in HBM and the frame left in HBM (device-timed: one CUDA-event pair around
            the K steps on the library's stream, three frames in flight, L2 flushed between steps inside the region).
@@ -536,7 +538,7 @@ def run_ours(args):
                     traffic = None
             r = roof(dom)
             kernels = {"sort": "k_depth_cull+k_radix_{hist,scan,scatter}<D1,D2>", "project": "k_project",
-                       "bin": "k_count+k_emit+tile radix passes+k_tile_ranges", "raster": "k_raster"}
+                       "bin": "k_count+k_emit_entries+k_radix_{hist,scan,scatter}<T1>(+<T2>+k_tile_ranges above 256 bins)", "raster": "k_raster"}
             res = {
                 "metric": METRICS.get(name, METRIC), "value": fps, "unit": "frames/s", "ms_per_step": ms_per_step,
                 "config": dict(config_block(args, name, n, w, h, orbit), parallelism=parallelism_label(world, args.exchange, mode)),
