@@ -360,3 +360,22 @@ def test_slab_path_random_regimes(gs, orc, ctx, monkeypatch):
                 order = orc.sort(m, fr.view, fr.cutout)
                 exp, _ = orc.render(cs, cc, order, fr.proj, fr.modelview, w, h, fr.focal, bg=bg)
                 assert len(order) == nsort and np.abs(ref - exp).max() <= FRAME_TOL
+
+
+def test_largest_frame_4096(gs, orc, ctx):
+    """4096 x 4096 is the largest frame the ABI accepts: 65 536 tiles, 43 x 43 bins (two bin passes), frame compared with
+    the oracle on a band of rows and on the RGBA8 / float consistency of the rest."""
+    w = h = 4096
+    rows, cs, cc, m, fr = scene_inputs(gs, orc, 40000, 4096, w, h)
+    ctx.clear(); ctx.push_packed(cs, cc, m[:, 15])
+    order = orc.sort(m, fr.view)
+    got = ctx.render(fr, fmt=gs.GS_FORMAT_RGBA32F, bg=(0.0, 0.0, 0.0, 1.0))
+    st = ctx.stats()
+    assert st["n_tiles"] == 256 * 256 and st["width"] == w
+    band = (h // 2 - 64, h // 2 + 64)
+    exp, _ = orc.render(cs, cc, order, fr.proj, fr.modelview, w, h, fr.focal, bg=(0.0, 0.0, 0.0, 1.0), rows=band)
+    assert np.abs(got[band[0]:band[1]] - exp[band[0]:band[1]]).max() <= FRAME_TOL
+    got8 = ctx.render(fr, fmt=gs.GS_FORMAT_RGBA8, bg=(0.0, 0.0, 0.0, 1.0))
+    assert np.abs(got8.astype(np.int32) - np.floor(np.clip(got, 0, 1) * 255 + 0.5).astype(np.int32)).max() <= 1
+    with pytest.raises(Exception):
+        ctx.render(gs.FrameInputs(proj=fr.proj, modelview=fr.modelview, view=fr.view, width=4097, height=16, focal=fr.focal))
