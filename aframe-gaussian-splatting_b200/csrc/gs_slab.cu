@@ -47,21 +47,27 @@ __global__ void __launch_bounds__(256) k_keys(const float *__restrict__ depth, c
   DepthRange dr{0.0, 0.0};
   if (ctr->sort.n_valid) dr = load_depth_range(ctr);
   uint32_t in = 0, drop = 0;
-  for (uint32_t i = blockIdx.x * blockDim.x + tid; i < n; i += gridDim.x * blockDim.x) {
-    const float d = __ldg(depth + i);
-    uint32_t key = kNoKey;
-    if (d != GS_DEPTH_REJECT) {
-      const int32_t k = depth_key(d, dr.min_depth, dr.depth_inv);
-      if (k >= 0 && k <= 65535) {
-        key = (uint32_t)k;
-        atomicAdd(&h[key >> 4], 1u);
-        ++in;
-      } else {
-        ++drop;  // typed-array write out of range: dropped (quirk Q5)
-      }
+  auto key_of = [&](float d) -> uint32_t {
+    if (d == GS_DEPTH_REJECT) return kNoKey;
+    const int32_t k = depth_key(d, dr.min_depth, dr.depth_inv);
+    if (k >= 0 && k <= 65535) {
+      atomicAdd(&h[(uint32_t)k >> 4], 1u);
+      ++in;
+      return (uint32_t)k;
     }
-    key32[i] = key;
+    ++drop;  // typed-array write out of range: dropped (quirk Q5)
+    return kNoKey;
+  };
+  // four splats per thread and step: the loads of a step are independent, so a thread keeps 16 B in flight instead
+  // of 4 (one load per dependent iteration made this pass latency-bound: 20 % of the HBM peak at 80 M splats)
+  const uint32_t n4 = n & ~3u;
+  for (uint32_t i = (blockIdx.x * blockDim.x + tid) * 4u; i < n4; i += gridDim.x * blockDim.x * 4u) {
+    const float4 d = __ldg((const float4 *)(depth + i));
+    uint4 k;
+    k.x = key_of(d.x); k.y = key_of(d.y); k.z = key_of(d.z); k.w = key_of(d.w);
+    *(uint4 *)(key32 + i) = k;
   }
+  if (blockIdx.x == 0 && tid < n - n4) key32[n4 + tid] = key_of(__ldg(depth + n4 + tid));
   for (int o = 16; o > 0; o >>= 1) {
     in += __shfl_xor_sync(0xffffffffu, in, o);
     drop += __shfl_xor_sync(0xffffffffu, drop, o);
@@ -327,7 +333,7 @@ static int grid_for(gs_context *c, uint64_t n, int per_cta, int per_sm) {
 
 void launch_keys(gs_context *c, const FrameParams *fp, FrameCounters *ctr, int set, cudaStream_t st) {
   cudaMemsetAsync(c->slab_tab[set], 0, sizeof(SlabTable), st);
-  k_keys<<<grid_for(c, c->cap, 256 * 8, 4), 256, 0, st>>>(c->depth, fp, ctr, c->key32[set], c->slab_tab[set]);
+  k_keys<<<grid_for(c, c->cap, 256 * 8, 8), 256, 0, st>>>(c->depth, fp, ctr, c->key32[set], c->slab_tab[set]);
 }
 
 void launch_slab_plan(gs_context *c, const FrameParams *fp, FrameCounters *ctr, int set, uint32_t first_target, int n_slabs,

@@ -29,9 +29,7 @@ __global__ void __launch_bounds__(256) k_depth_cull(const float4 *__restrict__ c
   double dmin = INFINITY, dmax = -INFINITY;
   uint32_t cnt = 0;
   const uint32_t stride = gridDim.x * blockDim.x;
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    const float4 c = __ldg(cs + i);
-    const float s = __ldg(sa + i);
+  auto process = [&](uint32_t i, const float4 c, const float s) {
     const double x = c.x, y = c.y, z = c.z;
     // index.js:519-523
     const double depth =
@@ -62,6 +60,21 @@ __global__ void __launch_bounds__(256) k_depth_cull(const float4 *__restrict__ c
       if (depth < dmin) dmin = depth;
     }
     depth_out[i] = out;
+  };
+  // two splats per thread and step, loads first: twice the bytes in flight per thread (the pass is a pure stream)
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += 2 * stride) {
+    const uint32_t j = i + stride;
+    const bool two = j < n;
+    const float4 c0 = __ldg(cs + i);
+    const float s0 = __ldg(sa + i);
+    float4 c1 = c0;
+    float s1 = s0;
+    if (two) {
+      c1 = __ldg(cs + j);
+      s1 = __ldg(sa + j);
+    }
+    process(i, c0, s0);
+    if (two) process(j, c1, s1);
   }
   // block reduction
   for (int o = 16; o > 0; o >>= 1) {
