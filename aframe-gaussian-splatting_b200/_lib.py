@@ -23,6 +23,7 @@ class GsStats(C.Structure):
         ("ms_total", C.c_float), ("kernel_launches", C.c_uint32), ("n_instances_kept", C.c_uint32),
         ("n_tile_instances", C.c_uint64), ("n_records_streamed", C.c_uint64), ("n_pair_tests", C.c_uint64),
         ("n_pair_hits", C.c_uint64),
+        ("n_slabs", C.c_uint32), ("n_slabs_run", C.c_uint32), ("n_slab_entries", C.c_uint64),
     ]
 
     def as_dict(self):

@@ -148,12 +148,14 @@ static int ensure_tile_stats(gs_context *c, uint32_t n_tiles) {
 // buffers of the front-to-back slab path (gs_slab.cu); the pipeline is idle when this runs
 static int ensure_slab(gs_context *c, uint32_t n_tiles, uint32_t n_bins) {
   if (c->slab_cap < c->cap || !c->key32[0]) {
-    dev_free(c->key32[0]); dev_free(c->key32[1]); dev_free(c->cidx); dev_free(c->ckey); dev_free(c->chunk_cnt);
+    dev_free(c->key32[0]); dev_free(c->key32[1]); dev_free(c->cidx); dev_free(c->ckey); dev_free(c->chunk_cnt[0]); dev_free(c->chunk_cnt[1]);
     GS_CUDA(c, dev_alloc(&c->key32[0], (size_t)c->cap + 8));
     GS_CUDA(c, dev_alloc(&c->key32[1], (size_t)c->cap + 8));
     GS_CUDA(c, dev_alloc(&c->cidx, (size_t)c->cap));
     GS_CUDA(c, dev_alloc(&c->ckey, (size_t)c->cap));
-    GS_CUDA(c, dev_alloc(&c->chunk_cnt, (size_t)c->cap / 2048 + 4));
+    c->chunk_row = (uint32_t)(c->cap / 2048 + 4);
+    GS_CUDA(c, dev_alloc(&c->chunk_cnt[0], (size_t)c->chunk_row * kMaxSlabs));
+    GS_CUDA(c, dev_alloc(&c->chunk_cnt[1], (size_t)c->chunk_row * kMaxSlabs));
     c->slab_cap = c->cap;
   }
   for (int i = 0; i < 2; ++i)
@@ -323,7 +325,7 @@ extern "C" int gs_destroy(gs_context *c) {
   if (c->peer_local) cudaFree(c->peer_local);
   dev_free(c->table_n); dev_free(c->table_d); dev_free(c->slice_total); dev_free(c->totals); dev_free(c->sort_hdr);
   dev_free(c->slice_prefix); dev_free(c->ent); dev_free(c->ent_off);
-  dev_free(c->key32[0]); dev_free(c->key32[1]); dev_free(c->cidx); dev_free(c->ckey); dev_free(c->chunk_cnt);
+  dev_free(c->key32[0]); dev_free(c->key32[1]); dev_free(c->cidx); dev_free(c->ckey); dev_free(c->chunk_cnt[0]); dev_free(c->chunk_cnt[1]);
   dev_free(c->slab_tab[0]); dev_free(c->slab_tab[1]);
   dev_free(c->pix_state); dev_free(c->tile_closed); dev_free(c->bin_open);
   for (auto &sl : c->slot) {
@@ -690,6 +692,7 @@ static cudaError_t enqueue_slab_keys_stage(gs_context *c, gs_context::Slot &sl, 
   launch_depth_cull(c, sl.fp, sl.ctr, st);
   launch_keys(c, sl.fp, sl.ctr, sl.set, st);
   launch_slab_plan(c, sl.fp, sl.ctr, sl.set, c->slab_first, sl.n_slabs, st);
+  launch_compact_offsets(c, sl.fp, sl.set, sl.n_slabs, st);  // one pass over the keys for every slab's compaction offsets
   if ((e = rec(sl.ev[1], st))) return e;
   return cudaGetLastError();
 }
@@ -766,7 +769,7 @@ static int launch_frame_slabs(gs_context *c, gs_context::Slot &sl, uint32_t n_ti
   }
   GS_CUDA(c, cudaEventRecord(sl.ev_binned, c->rstream));
   c->sort_set_free[set] = sl.ev_binned;
-  sl.launches = 4u + 1u + (uint32_t)n_slabs * (n_bins <= 256u ? 18u : 22u) + 2u;
+  sl.launches = 6u + 1u + (uint32_t)n_slabs * (n_bins <= 256u ? 16u : 20u) + 2u;
   return GS_OK;
 }
 
@@ -961,6 +964,9 @@ static int wait_slot(gs_context *c, gs_context::Slot &sl, gs_stats *stats) {
       rs += t;
     }
     c->stats.ms_project = 0.f;
+    c->stats.n_slabs = (uint32_t)sl.n_slabs;
+    c->stats.n_slabs_run = sl.ctr_host->slabs_run;
+    c->stats.n_slab_entries = sl.ctr_host->slab_entries;
     c->stats.ms_raster = rs + res;
     c->stats.ms_bin = loop - rs;
   } else {

@@ -73,6 +73,7 @@ struct FrameCounters {
   uint32_t slabs_run;          // slabs that found open bins and entries
   unsigned long long n_inst_total;  // bin-instance candidates, summed over the slabs
   unsigned long long n_inst_slab_max;  // ... of the largest slab (what the instance buffers must hold)
+  unsigned long long slab_entries;     // entries (real + Q5 repeats) of the slabs that ran: what was compacted, sorted, projected
 };
 static_assert(offsetof(FrameCounters, sort) == 0 && sizeof(SortHeader) == 32, "SortHeader is the prefix of FrameCounters");
 
@@ -181,7 +182,8 @@ struct gs_context {
   uint32_t *key32[2] = {nullptr, nullptr};  // [cap] 16-bit depth key of every splat, kNoKey if not in the sort (one per set)
   uint32_t *cidx = nullptr;        // [cap] splat indices of the current slab, in index order
   uint16_t *ckey = nullptr;        // [cap] their keys
-  uint32_t *chunk_cnt = nullptr;   // [cap / 2048 + 2] compaction offsets
+  uint32_t *chunk_cnt[2] = {nullptr, nullptr};  // [kMaxSlabs][chunk_row] per-slab compaction offsets of every 2048-splat chunk (one per set)
+  uint32_t chunk_row = 0;          // row stride of chunk_cnt: cap / 2048 + 4
   gs::SlabTable *slab_tab[2] = {nullptr, nullptr};
   float4 *pix_state = nullptr;     // [tiles * 256] {R, G, B, T} carried from slab to slab
   uint8_t *tile_closed = nullptr;  // [tiles]
@@ -318,7 +320,8 @@ void launch_peer_release(gs_context *c, const PeerRows &rows, uint32_t world, ui
 void launch_keys(gs_context *c, const FrameParams *fp, FrameCounters *ctr, int set, cudaStream_t st);  // keys + bucket histogram
 void launch_slab_plan(gs_context *c, const FrameParams *fp, FrameCounters *ctr, int set, uint32_t first_target, int n_slabs, cudaStream_t st);
 void launch_slab_init(gs_context *c, const FrameParams *fp, FrameCounters *ctr, cudaStream_t st);
-void launch_slab_begin(gs_context *c, const FrameParams *fp, FrameCounters *ctr, int set, int slab, cudaStream_t st);  // + compaction: 4 launches
+void launch_compact_offsets(gs_context *c, const FrameParams *fp, int set, int n_slabs, cudaStream_t st);  // every slab's chunk offsets: 2 launches
+void launch_slab_begin(gs_context *c, const FrameParams *fp, FrameCounters *ctr, int set, int slab, cudaStream_t st);  // + compaction: 2 launches
 void launch_slab_sort(gs_context *c, const FrameParams *fp, FrameCounters *ctr, const FrameBufs &b, cudaStream_t st);  // 6 launches
 void launch_project_entries(gs_context *c, const FrameParams *fp, FrameCounters *ctr, const FrameBufs &b, cudaStream_t st);
 void launch_emit_slab(gs_context *c, const FrameParams *fp, FrameCounters *ctr, const FrameBufs &b, cudaStream_t st);

@@ -10,9 +10,10 @@
 //   once per frame   k_keys        the reference's 16-bit key of every sorted splat (index.js:561) + a 4096-bucket histogram
 //                    k_slab_plan   slab boundaries on the key axis, nearest first: ~1 M, 2 M, 4 M ... entries
 //                    k_slab_init   per-pixel state {R, G, B, T}, per-tile closed flags, per-bin live-tile counts
+//                    k_compact_count_all / k_compact_scan_all   every slab's per-chunk compaction offsets, one pass over the keys
 //   per slab         k_slab_begin  entry count of the slab; 0 when no bin is open any more (every later kernel then
 //                                  finds nothing to do)
-//                    k_compact_*   the slab's splats (keys in [klo, khi)) in index order
+//                    k_compact_write  the slab's splats (keys in [klo, khi)) in index order
 //                    radix S1, D2  stable sort by the 16-bit key -> the reference's draw order restricted to the slab
 //                    k_project     vertex shader for the slab's entries only
 //                    k_count/emit  bin instances, skipping closed bins; stable sort by bin; per-bin ranges
@@ -185,7 +186,10 @@ __global__ void k_slab_begin(const SlabTable *__restrict__ tab, FrameCounters *c
   ctr->n_inst = 0;
   ctr->n_inst_kept = 0;
   ctr->count_done = 0;
-  if (active) ctr->slabs_run += 1;
+  if (active) {
+    ctr->slabs_run += 1;
+    ctr->slab_entries += m;
+  }
 }
 
 // frame totals back into the counters the host reads
@@ -211,40 +215,52 @@ __device__ __forceinline__ void load_keys8(const uint32_t *__restrict__ key32, u
   }
 }
 
-__global__ void __launch_bounds__(kCompactThreads) k_compact_count(const uint32_t *__restrict__ key32,
-                                                                   const FrameParams *__restrict__ fp,
-                                                                   const FrameCounters *__restrict__ ctr,
-                                                                   const SlabTable *__restrict__ tab, int slab,
-                                                                   uint32_t *__restrict__ cnt) {
-  if (!ctr->slab_real) return;
-  __shared__ uint32_t s_w[kCompactThreads / 32];
-  const uint32_t n = fp->n_splats, lo = tab->klo[slab], hi = tab->khi[slab];
+// Chunk counts of EVERY scheduled slab in one pass over the keys (stage A, after the plan): slab boundaries are bucket
+// aligned, so a 4096-entry table maps a key to its slab; a thread tallies its 8 keys in 4-bit fields of one 64-bit
+// word (12 slabs x 4 bits, at most 8 per field), the warp adds each field with redux.  cnt[s * row + c] = entries of
+// slab s in chunk c.  (A pass per slab read the 4 B keys of all N splats once more for every slab that ran.)
+__global__ void __launch_bounds__(kCompactThreads) k_compact_count_all(const uint32_t *__restrict__ key32,
+                                                                       const FrameParams *__restrict__ fp,
+                                                                       const SlabTable *__restrict__ tab, int n_slabs,
+                                                                       uint32_t *__restrict__ cnt, uint32_t row) {
+  __shared__ uint8_t s_slab[kSlabBuckets];
+  __shared__ uint32_t s_klo[kMaxSlabs];
+  __shared__ uint32_t s_c[kMaxSlabs];
+  const uint32_t tid = threadIdx.x, lane = tid & 31u;
+  if (tid < (uint32_t)kMaxSlabs) s_klo[tid] = tab->klo[tid];
+  __syncthreads();
+  for (uint32_t b = tid; b < (uint32_t)kSlabBuckets; b += blockDim.x) {
+    uint32_t sid = 0;  // slabs run from the high keys down: the slab of bucket b is the number of slabs that end above it
+    for (int s = 0; s < n_slabs; ++s) sid += (b * 16u < s_klo[s]) ? 1u : 0u;
+    s_slab[b] = (uint8_t)min(sid, (uint32_t)(kMaxSlabs - 1));
+  }
+  const uint32_t n = fp->n_splats;
   const uint32_t nchunks = (n + kCompactChunk - 1) / kCompactChunk;
-  const uint32_t tid = threadIdx.x;
   for (uint32_t c = blockIdx.x; c < nchunks; c += gridDim.x) {
-    uint32_t k[8], m = 0;
+    if (tid < (uint32_t)kMaxSlabs) s_c[tid] = 0;
+    __syncthreads();  // also orders the table build before its first use
+    uint32_t k[8];
     load_keys8(key32, c * kCompactChunk + tid * kCompactItems, n, k);
+    unsigned long long m = 0ull;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) m += (k[j] >= lo && k[j] < hi) ? 1u : 0u;
-    for (int o = 16; o > 0; o >>= 1) m += __shfl_xor_sync(0xffffffffu, m, o);
-    if ((tid & 31u) == 0) s_w[tid >> 5] = m;
-    __syncthreads();
-    if (tid == 0) {
-      uint32_t t = 0;
-      for (int w = 0; w < kCompactThreads / 32; ++w) t += s_w[w];
-      cnt[c] = t;
+    for (int j = 0; j < 8; ++j)
+      if (k[j] < 65536u) m += 1ull << (4u * s_slab[k[j] >> 4]);
+    for (int s = 0; s < n_slabs; ++s) {
+      const uint32_t v = __reduce_add_sync(0xffffffffu, (uint32_t)(m >> (4 * s)) & 15u);
+      if (lane == 0 && v) atomicAdd(&s_c[s], v);
     }
     __syncthreads();
+    if (tid < (uint32_t)n_slabs) cnt[tid * row + c] = s_c[tid];
   }
 }
 
-// exclusive scan of the chunk counts, one CTA; every thread owns 16 consecutive counts per round
-__global__ void __launch_bounds__(1024) k_compact_scan(uint32_t *__restrict__ cnt, const FrameParams *__restrict__ fp,
-                                                       const FrameCounters *__restrict__ ctr) {
-  if (!ctr->slab_real) return;
+// exclusive scan of every slab's chunk counts: CTA s scans row s; every thread owns 16 consecutive counts per round
+__global__ void __launch_bounds__(1024) k_compact_scan_all(uint32_t *__restrict__ cnt_all, const FrameParams *__restrict__ fp,
+                                                           uint32_t row) {
   constexpr uint32_t kPer = 16;
   __shared__ uint32_t s_w[32];
   __shared__ uint32_t s_carry;
+  uint32_t *__restrict__ cnt = cnt_all + (size_t)blockIdx.x * row;
   const uint32_t nchunks = (fp->n_splats + kCompactChunk - 1) / kCompactChunk;
   const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
   if (tid == 0) s_carry = 0;
@@ -347,12 +363,18 @@ void launch_slab_init(gs_context *c, const FrameParams *fp, FrameCounters *ctr, 
                                                                                            c->bin_open);
 }
 
+// stage A, after the plan: chunk offsets of every scheduled slab (the loop's k_compact_write reads row `slab`)
+void launch_compact_offsets(gs_context *c, const FrameParams *fp, int set, int n_slabs, cudaStream_t st) {
+  const int grid = grid_for(c, c->cap, kCompactChunk, 8);
+  k_compact_count_all<<<grid, kCompactThreads, 0, st>>>(c->key32[set], fp, c->slab_tab[set], n_slabs, c->chunk_cnt[set], c->chunk_row);
+  k_compact_scan_all<<<n_slabs, 1024, 0, st>>>(c->chunk_cnt[set], fp, c->chunk_row);
+}
+
 void launch_slab_begin(gs_context *c, const FrameParams *fp, FrameCounters *ctr, int set, int slab, cudaStream_t st) {
   k_slab_begin<<<1, 32, 0, st>>>(c->slab_tab[set], ctr, slab);
   const int grid = grid_for(c, c->cap, kCompactChunk, 8);
-  k_compact_count<<<grid, kCompactThreads, 0, st>>>(c->key32[set], fp, ctr, c->slab_tab[set], slab, c->chunk_cnt);
-  k_compact_scan<<<1, 1024, 0, st>>>(c->chunk_cnt, fp, ctr);
-  k_compact_write<<<grid, kCompactThreads, 0, st>>>(c->key32[set], fp, ctr, c->slab_tab[set], slab, c->chunk_cnt, c->cidx, c->ckey);
+  k_compact_write<<<grid, kCompactThreads, 0, st>>>(c->key32[set], fp, ctr, c->slab_tab[set], slab,
+                                                    c->chunk_cnt[set] + (size_t)slab * c->chunk_row, c->cidx, c->ckey);
 }
 
 void launch_slab_end(gs_context *c, FrameCounters *ctr, cudaStream_t st) { k_slab_end<<<1, 32, 0, st>>>(ctr); }

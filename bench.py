@@ -65,6 +65,15 @@ def algorithmic_bytes(st: dict) -> dict:
     # culls per tile inside the raster, so it MOVES fewer bytes than this formula charges.
     N, V, V2, D, T = st["n_splats"], st["n_sorted"], st["n_visible"], st["n_tile_instances"], st["n_tiles"]
     P = st["width"] * st["height"]
+    if st.get("n_slabs"):
+        # front-to-back slab path: the one-pass formula would charge work this path never does (bins that
+        # closed), so the bytes are those of the passes it really needs.  R slabs ran over E draw-order entries, K bin
+        # instances were kept.
+        R, E, K = st["n_slabs_run"], st["n_slab_entries"], st["n_instances_kept"]
+        a = 20 * N + 8 * N + 4 * N + 4 * N    # cull read, fp32 depth out and back in (range first, then key), key write, offsets pass
+        b = R * 4 * N + E * (6 + 24 + 24 + 32) + 80 * K + 8 * T * R  # per slab: key scan; per entry: compact, 2 radix passes, project
+        r = 36 * K + 32 * P + 4 * P           # records + pixel state once + the frame
+        return {"sort": a, "project": 0, "bin": b, "raster": r, "total": a + b + r}
     return {
         "sort": 20 * N + 8 * V,               # K1: 16 B centre + 4 B sizeAlpha read, depth + index write
         "project": 8 * V + 16 * V + 32 * V2,  # K2 (without the key emission, counted under bin)
@@ -515,7 +524,8 @@ def run_ours(args):
         res = None
         if rank == 0:
             st = {k: float(np.mean([s[k] for s in lat_stats])) for k in lat_stats[0]}
-            for k in ("n_splats", "n_sorted", "n_visible", "n_instances", "n_instances_kept", "n_tiles", "width", "height", "kernel_launches", "n_dropped"):
+            for k in ("n_splats", "n_sorted", "n_visible", "n_instances", "n_instances_kept", "n_tiles", "width", "height", "kernel_launches", "n_dropped",
+                      "n_slabs", "n_slabs_run", "n_slab_entries"):
                 st[k] = int(lat_stats[0][k])
             for k2 in ("n_tile_instances", "n_records_streamed", "n_pair_tests", "n_pair_hits"):
                 st[k2] = int(full_stats[k2])
@@ -537,6 +547,11 @@ def run_ours(args):
                 except Exception:
                     traffic = None
             r = roof(dom)
+            slab_info = None
+            if st["n_slabs"]:
+                slab_info = {"scheduled": st["n_slabs"], "run": st["n_slabs_run"], "entries": st["n_slab_entries"],
+                             "note": "front-to-back slab path: stages are keys (sort) / slab loop without its rasters (bin) / rasters + resolve; "
+                                     "bytes per stage are the slab path's own passes (bench.py algorithmic_bytes), not the one-pass formula"}
             kernels = {"sort": "k_depth_cull+k_radix_{hist,scan,scatter}<D1,D2>", "project": "k_project",
                        "bin": "k_count+k_emit_entries+k_radix_{hist,scan,scatter}<T1>(+<T2>+k_tile_ranges above 256 bins)", "raster": "k_raster"}
             res = {
@@ -563,6 +578,11 @@ def run_ours(args):
                 "push": {"msplats_per_s": n / t_push / 1e6, "n": n, "ms": 1000 * t_push,
                          "note": "gs_push_splats of raw 32 B rows from pageable host memory in 4 M-row chunks, device-side pack included"},
             }
+            if slab_info:
+                res["slabs"] = slab_info
+                res["roofline"]["kernel"] = {"sort": "k_depth_cull+k_keys+k_slab_plan+k_compact_count_all+k_compact_scan_all",
+                                             "bin": "per slab: k_compact_write+k_radix<S1,D2>+k_project<entries>+k_count+k_emit_entries+k_radix<T1>",
+                                             "raster": "k_raster<slab> per slab + k_resolve", "project": "-"}[dom]
             if frame_check is not None:
                 res["frame_check"] = frame_check
             if world == 1 and not args.no_cpu_baseline:

@@ -95,6 +95,9 @@ typedef struct gs_stats {
   uint64_t n_records_streamed;/*  (STATS) bin records the raster CTAs pulled through shared memory            */
   uint64_t n_pair_tests;    /*    (STATS) pixel-splat pairs evaluated by live pixels                          */
   uint64_t n_pair_hits;     /*    (STATS) pairs that passed r^2 <= 4 (and the depth test) and were blended   */
+  uint32_t n_slabs;         /*    front-to-back slab path (large scenes): depth slabs scheduled; 0 = one-pass frame */
+  uint32_t n_slabs_run;     /*    ... slabs that still found an open bin (the others launch and find nothing to do) */
+  uint64_t n_slab_entries;  /*    ... draw-order entries of the slabs that ran: compacted, sorted and projected      */
 } gs_stats;
 
 /* ---- lifetime ---------------------------------------------------------------------------- */

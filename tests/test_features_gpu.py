@@ -256,6 +256,9 @@ def test_slab_path_equals_one_pass(gs, orc, ctx, monkeypatch, n, w, h, first):
         assert np.array_equal(c.render(fr, bg=bg, fmt=gs.GS_FORMAT_RGBA32F, depth_in=depth), refd)
         assert st["n_sorted"] == len(order) == st_ref["n_sorted"] and st["n_splats"] == n
         assert st["kernel_launches"] > 40  # several slabs were scheduled
+        assert 1 <= st["n_slabs_run"] <= st["n_slabs"] <= 12 and st_ref["n_slabs"] == 0
+        # every slab that ran was compacted, sorted and projected: at least the nearest slab, at most the whole sort
+        assert min(first, len(order)) * 0.5 <= st["n_slab_entries"] <= len(order) + st["n_dropped"]
         # pipelined: three slab frames in flight, different cameras
         sc = gs.scenes
         frames = [sc.make_frame(sc.orbit_camera(w, h, s), sc.demo_object(), w, h) for s in (0, 9, 33, 77)]

@@ -35,7 +35,7 @@ def test_no_cpu_fallback_without_gpu(gs):
 def test_struct_layouts_match_header(gs):
     assert ctypes.sizeof(gs.GsRenderParams) == 16 * 4 * 2 + 4 + 4 + 4 + 16 + 4 + 64 + 4 + 4 + 8  # + depth_in pointer
     assert gs.GsRenderParams.depth_in.offset == 232
-    assert ctypes.sizeof(gs.GsStats) == 88 + 4 * 8  # + n_tile_instances, n_records_streamed, n_pair_tests, n_pair_hits
+    assert ctypes.sizeof(gs.GsStats) == 88 + 4 * 8 + 16  # + the four STATS sums + n_slabs, n_slabs_run, n_slab_entries
 
 
 def test_owned_tiles_partition(gs):
