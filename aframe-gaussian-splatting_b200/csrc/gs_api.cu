@@ -570,7 +570,7 @@ static cudaError_t enqueue_sort_stage(gs_context *c, gs_context::Slot &sl, bool 
   if ((e = cudaEventRecord(c->ev_fork[0], m))) return e;
   if ((e = cudaStreamWaitEvent(x, c->ev_fork[0], 0))) return e;
   if ((e = rec(sl.evp[0], x))) return e;
-  launch_project(c, sl.fp, b, x);
+  launch_project(c, sl.fp, sl.ctr, b, x);
   if ((e = rec(sl.evp[1], x))) return e;
   if ((e = cudaEventRecord(c->ev_join[0], x))) return e;
   if (!reuse) {

@@ -149,6 +149,7 @@ def _check_projection(gs, orc, ctx, cs, cc, fr, order):
 
 @pytest.mark.parametrize("n,w,h,cutout,fmt", [
     (64, 256, 144, False, "f32"), (20000, 256, 144, False, "f32"), (20000, 250, 141, True, "f32"),
+    (4099, 250, 141, True, "f32"),  # sparse-frame projection path (cutout keeps < half), chunk tail not a multiple of 4
     (150000, 1920, 1080, False, "f32"), (150000, 1920, 1080, False, "u8"), (60000, 3840, 2160, True, "u8"),
 ])
 def test_render_parity(gs, orc, ctx, n, w, h, cutout, fmt):
