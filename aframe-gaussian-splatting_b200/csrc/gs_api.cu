@@ -245,7 +245,7 @@ extern "C" int gs_create(int device_ordinal, gs_context **out_ctx) {
   for (int i = 0; i < 2; ++i)
     if ((e = cudaEventCreateWithFlags(&c->push_ev[i], cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
   if ((e = cudaEventCreateWithFlags(&c->push_done, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
-  for (int i = 0; i < 3; ++i) c->slot[i].index = i;
+  for (int i = 0; i < gs_context::kSlots; ++i) c->slot[i].index = i;
   if ((e = cudaStreamCreateWithPriority(&c->aux_stream, cudaStreamNonBlocking, prio_greatest)) != cudaSuccess) return bail("cudaStreamCreate", e);
   for (int i = 0; i < 2; ++i) {
     if ((e = cudaEventCreateWithFlags(&c->ev_fork[i], cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
@@ -992,9 +992,14 @@ extern "C" int gs_render_async(gs_context *c, const gs_render_params *p, void *o
   const uint32_t n_bins = ((p->width + kBin - 1) / kBin) * ((p->height + kBin - 1) / kBin);  // <= 64*64: fits the 16-bit bin id
   GS_CUDA(c, cudaSetDevice(c->device));
   const uint64_t ticket = c->next_ticket;
-  gs_context::Slot &sl = c->slot[ticket % 3];
+  gs_context::Slot &sl = c->slot[ticket % gs_context::kSlots];
   int rcode;
   if (sl.pending && (rcode = wait_slot(c, sl, nullptr))) return rcode;  // slot reuse: its previous frame must be done
+  if ((p->flags & GS_RENDER_OUT_PEER) && ticket >= 3) {
+    // the shared frame ring of the fused exchange has three entries, released by gs_wait: at most three such frames
+    gs_context::Slot &o = c->slot[(ticket - 3) % gs_context::kSlots];
+    if (o.pending && o.ticket == ticket - 3 && (rcode = wait_slot(c, o, nullptr))) return rcode;
+  }
   if ((p->flags & GS_RENDER_REUSE_SORT) && c->have_order && (rcode = drain(c))) return rcode;  // runs in the last sort's buffers
   if ((p->flags & GS_RENDER_STATS) && (rcode = drain(c))) return rcode;  // the per-tile statistics buffer is not double-buffered
   // large scenes render front to back in depth slabs; the two paths share scratch buffers, so a change drains
@@ -1042,8 +1047,8 @@ extern "C" int gs_wait(gs_context *c, uint64_t ticket, gs_stats *stats) {
   if (!c) return GS_ERR_INVALID;
   if (ticket >= c->next_ticket) return fail(c, GS_ERR_INVALID, "gs_wait: unknown ticket");
   GS_CUDA(c, cudaSetDevice(c->device));
-  gs_context::Slot &sl = c->slot[ticket % 3];
-  if (ticket + 3 < c->next_ticket || !sl.pending) {  // already completed (e.g. by a slot-reuse wait): stats of that frame are gone, frame is in place
+  gs_context::Slot &sl = c->slot[ticket % gs_context::kSlots];
+  if (ticket + gs_context::kSlots < c->next_ticket || !sl.pending || sl.ticket != ticket) {  // already completed (e.g. by a slot-reuse wait): stats of that frame are gone, frame is in place
     if (stats) *stats = c->stats;
     return GS_OK;
   }
@@ -1113,7 +1118,7 @@ extern "C" int gs_peer_import(gs_context *c, uint32_t rank, uint32_t world, cons
 
 extern "C" int gs_peer_frame(gs_context *c, uint64_t ticket, void **out) {
   if (!c || !out || !c->peer_local || ticket >= c->next_ticket || ticket + 3 < c->next_ticket) return GS_ERR_INVALID;
-  const gs_context::Slot &sl = c->slot[ticket % 3];
+  const gs_context::Slot &sl = c->slot[ticket % gs_context::kSlots];
   if (!sl.peer || sl.ticket != ticket) return GS_ERR_INVALID;
   *out = peer_frame(c->peer_local, c->peer_frame_bytes, sl.ring);
   return GS_OK;

@@ -203,7 +203,12 @@ struct gs_context {
   int quirk_n = 0;
   gs::SortHeader *sort_hdr = nullptr;  // device: counters header of the last sort (for GS_RENDER_REUSE_SORT)
 
-  // ---- three pipeline slots (ticket % 3): frame k is rasterised while k+1 is binned, k+2 sorted and k-1 copied to the host ----
+  // ---- pipeline slots (ticket % kSlots): frame k is rasterised while k+1 is binned, k+2 is sorted and k-1 is copied to
+  // the host.  Three stages + the copy = four frames a caller can have outstanding; the GPU-side order of the stages is
+  // kept by the buffer-set events below, a slot only holds a frame's parameters, counters, events and output staging.
+  // (With three slots a caller that receives frames in host memory had to collect frame k-1's copy before it could
+  // submit frame k+2, and the sort stage idled for the length of the copy: 3 200 instead of 3 800 frames/s.) ----
+  static constexpr int kSlots = 4;
   struct Slot {
     gs::FrameCounters *ctr = nullptr;        // device
     gs::FrameCounters *ctr_host = nullptr;   // pinned
@@ -245,7 +250,7 @@ struct gs_context {
     gs_render_params params{};
     uint32_t launches = 0;
     int set = 0;                                    // which order/proj_rec/rect and inst_rec/bin_range copy it uses
-  } slot[3];
+  } slot[kSlots];
   uint64_t next_ticket = 0;
   cudaStream_t bstream = nullptr;                   // binning stage (high priority, like the sort stage's `stream`)
   cudaEvent_t sort_set_free[2] = {nullptr, nullptr};  // last binning stage that read order/proj_rec/rect[i]

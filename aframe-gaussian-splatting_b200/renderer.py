@@ -171,7 +171,7 @@ class SplatContext:
         return st
 
     def render_async(self, params: GsRenderParams, out_ptr: int) -> int:
-        """gs_render_async: enqueue one frame, return its ticket (three frames may be in flight)."""
+        """gs_render_async: enqueue one frame, return its ticket (four frames may be outstanding: three stages + the copy to the host)."""
         t = C.c_uint64()
         self._check(self._lib.gs_render_async(self._h, C.byref(params), C.c_void_p(out_ptr), C.byref(t)))
         return t.value

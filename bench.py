@@ -363,7 +363,7 @@ def run_ours(args):
         p_host = [ctx.make_params(f, fmt=gs.GS_FORMAT_RGBA8, flags=0) for f in frames]
         nf = len(frames)
         with torch.cuda.stream(stream):
-            frames_dev = [torch.zeros(h * w * 4, dtype=torch.uint8, device=dev) for _ in range(3)]
+            frames_dev = [torch.zeros(h * w * 4, dtype=torch.uint8, device=dev) for _ in range(4)]
             tiles_bufs = [torch.zeros(tiles_per_rank * 1024, dtype=torch.uint8, device=dev) for _ in range(3)] if sharded else None
             gath_bufs = [torch.zeros(world * tiles_per_rank * 1024, dtype=torch.uint8, device=dev) for _ in range(3)] if sharded else None
         stream.synchronize()
@@ -397,16 +397,17 @@ def run_ours(args):
             if use_peer:
                 return ctx.render_async(peer_dev, 1)  # the assembled frame lands in the shared ring
             if not sharded:
-                return ctx.render_async(p_dev[fidx(i)], frames_dev[i % 3].data_ptr())
+                return ctx.render_async(p_dev[fidx(i)], frames_dev[i % 4].data_ptr())
             t = ctx.render_async(p_dev[i % nf], tiles_bufs[i % 3].data_ptr())
             with torch.cuda.stream(stream):
                 dist.all_gather_into_tensor(gath_bufs[i % 3], tiles_bufs[i % 3])
             ctx.assemble_tiles(gath_bufs[i % 3].data_ptr(), tiles_per_rank, world, w, h, gs.GS_FORMAT_RGBA8, frames_dev[i % 3].data_ptr())
             return t
 
-        def run_pipeline(submit, k, collect=None):
-            """k frames, at most three in flight; one CUDA-event pair on the library's stream brackets everything (the L2
-            flushes between steps included)."""
+        def run_pipeline(submit, k, collect=None, depth=3):
+            """k frames, at most `depth` outstanding (3: sort(i) | bin(i-1) | raster(i-2); 4 when frames also cross PCIe:
+            + copy(i-3)); one CUDA-event pair on the library's stream brackets everything (the L2 flushes between steps
+            included)."""
             r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             tickets = []
             with torch.cuda.stream(stream):
@@ -415,11 +416,11 @@ def run_ours(args):
                 with torch.cuda.stream(stream):
                     flush.zero_()  # L2 flush between timed iterations
                 tickets.append(submit(i))
-                if i >= 2:  # three frames in flight: sort(i) | bin(i-1) | raster(i-2)
-                    st = ctx.wait(tickets[i - 2])
+                if i >= depth - 1:
+                    st = ctx.wait(tickets[i - (depth - 1)])
                     if collect is not None:
                         collect.append(st.as_dict())
-            for t in tickets[max(0, len(tickets) - 2):]:
+            for t in tickets[max(0, len(tickets) - (depth - 1)):]:
                 st = ctx.wait(t)
                 if collect is not None:
                     collect.append(st.as_dict())
@@ -440,7 +441,7 @@ def run_ours(args):
 
         # ---- value: device-resident frames ----
         barrier()
-        my_ms = run_pipeline(submit_device, steps)
+        my_ms = run_pipeline(submit_device, steps, depth=3 if sharded else args.value_depth)
         total_ms = allmax(my_ms)
         barrier()
         if world > 1:
@@ -462,10 +463,11 @@ def run_ours(args):
         full_stats = ctx.wait(ctx.render_async(p_stats, (tiles_bufs[0] if sharded else frames_dev[0]).data_ptr())).as_dict()
 
         # ---- e2e: host buffers through the public C-ABI call, copies inside the timed region ----
-        host_frames = [ctx.pinned_array((h, w, 4), np.uint8) for _ in range(3)]
+        host_frames = [ctx.pinned_array((h, w, 4), np.uint8) for _ in range(4)]
+        e2e_depth = 3 if sharded else 4  # the tile-sharded modes keep their three-entry exchange rings
         if not sharded:
             def submit_host(i):
-                return ctx.render_async(p_host[fidx(i)], host_frames[i % 3].ctypes.data)
+                return ctx.render_async(p_host[fidx(i)], host_frames[i % 4].ctypes.data)
         elif use_peer:
             def submit_host(i):
                 return ctx.render_async(peer_host, host_frames[i % 3].ctypes.data)
@@ -475,13 +477,14 @@ def run_ours(args):
                 with torch.cuda.stream(stream):  # frame back to pinned host memory, stream-ordered after the un-tiling
                     torch.from_numpy(host_frames[i % 3].reshape(-1)).copy_(frames_dev[i % 3], non_blocking=True)
                 return t
-        run_pipeline(submit_host, 3)
+        run_pipeline(submit_host, 4, depth=e2e_depth)
         barrier()
-        e2e_ms = allmax(run_pipeline(submit_host, steps)) / steps
+        e2e_ms = allmax(run_pipeline(submit_host, steps, depth=e2e_depth)) / steps
         barrier()
         e2e = {"value": units * 1000.0 / e2e_ms, "unit": "frames/s", "ms_per_step": e2e_ms,
                "h2d_bytes_per_step": units * C.sizeof(gs.GsRenderParams), "d2h_bytes_per_step": units * h * w * 4,
-               "note": "gs_render_async/gs_wait with host buffers, three frames in flight: the camera matrices go in as one small "
+               "frames_outstanding": e2e_depth,
+               "note": "gs_render_async/gs_wait with host buffers, up to four tickets open (sort | bin | raster | copy): the camera matrices go in as one small "
                        "H2D copy, the RGBA8 frame comes back to pinned host memory on a copy stream while the next frame renders; "
                        "the timed region (one CUDA-event pair around all K steps) includes every copy and the L2 flushes"}
 
@@ -652,6 +655,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="train_1m_1080p")
     ap.add_argument("--splats", type=int, default=0, help="override the workload's splat count (debug)")
+    ap.add_argument("--value-depth", type=int, default=3, choices=[3, 4], help="tickets kept open in the device-resident timing loop")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the oracle legs (parity block + cpu_baseline)")
     ap.add_argument("--no-other-configs", action="store_true", help="N = 1: time only the headline configuration")
     ap.add_argument("--parallel", default="auto", choices=["auto", "frames", "tiles"],

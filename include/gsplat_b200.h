@@ -191,12 +191,14 @@ GS_API int gs_render(gs_context *ctx, const gs_render_params *params, void *out_
  * Pipelined form of gs_render (= gs_render_async + gs_wait).  A frame is three stages on three internal streams,
  * each one CUDA graph: A depth sort + projection, B tile binning, C raster; its counters and (for a host out_rgba)
  * its RGBA frame are then copied to the host on a fourth stream.  gs_render_async enqueues all of that and returns
- * a ticket at once; gs_wait blocks until that frame is in out_rgba.  THREE frames may be in flight (slot =
- * ticket % 3): frame k is rasterised while frame k+1 is binned and frame k+2 sorted, and frame k-1 crosses PCIe
- * (the reference likewise overlaps its worker sort with drawing, index.js:206,439-440).  A FOURTH
- * gs_render_async first waits for the oldest frame.
+ * a ticket at once; gs_wait blocks until that frame is in out_rgba.  FOUR frames may be outstanding (slot =
+ * ticket % 4): frame k is rasterised while frame k+1 is binned and frame k+2 sorted, and frame k-1 crosses PCIe
+ * (the reference likewise overlaps its worker sort with drawing, index.js:206,439-440) - a caller that receives
+ * frames in host memory should keep four tickets open, so that collecting frame k-1's copy never delays the
+ * submission of frame k+2.  A FIFTH gs_render_async first waits for the oldest frame (GS_RENDER_OUT_PEER frames:
+ * a fourth, the shared frame ring has three entries).
  * Buffer lifetime: out_rgba (and any device buffer passed with GS_RENDER_OUT_DEVICE / _TILED) must stay valid and
- * untouched until gs_wait of that ticket returns, i.e. across up to three outstanding frames; use page-locked
+ * untouched until gs_wait of that ticket returns, i.e. across up to four outstanding frames; use page-locked
  * memory (gs_host_alloc) for a truly asynchronous copy.
  * gs_wait(ticket) on a ticket that was already retired (by an earlier gs_wait, or implicitly when its slot was
  * reused or the pipeline was drained by gs_clear / gs_sort / a growing push) returns GS_OK with the stats of the

@@ -267,6 +267,16 @@ def test_render_async_pipeline(gs, orc, ctx):
     assert all(np.array_equal(outs[i], ref[i]) for i in range(3))
     with pytest.raises(Exception):
         ctx.wait(t2 + 5)
+    # four tickets open at once (sort | bin | raster | copy to the host); a fifth and sixth submit recycle the oldest
+    # slots implicitly, and waiting on a ticket retired that way still returns GS_OK with the frame in place
+    for o in outs:
+        o[...] = 0
+    ts = [ctx.render_async(ctx.make_params(frames[i], fmt=gs.GS_FORMAT_RGBA8), outs[i].ctypes.data) for i in range(5)]
+    extra = ctx.pinned_array((360, 640, 4), np.uint8)
+    ts.append(ctx.render_async(ctx.make_params(frames[2], fmt=gs.GS_FORMAT_RGBA8), extra.ctypes.data))
+    for t in reversed(ts):
+        ctx.wait(t)
+    assert all(np.array_equal(outs[i], ref[i]) for i in range(5)) and np.array_equal(extra, ref[2])
     # the oracle agrees with what the pipeline produced
     exp, _ = orc.render(cs, cc, orc.sort(m, frames[3].view), frames[3].proj, frames[3].modelview, 640, 360, frames[3].focal)
     e8 = np.floor(np.clip(exp, 0, 1) * 255.0 + 0.5).astype(np.int32)
