@@ -30,3 +30,21 @@ def test_our_arm_needs_a_gpu():
     res = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "1"], capture_output=True, text=True,
                          timeout=300)
     assert res.returncode != 0 and "no CPU fallback" in (res.stderr + res.stdout)
+
+
+def test_algorithmic_bytes_one_pass_and_slab():
+    """SURVEY.md 8(d) byte model: the one-pass formula, and the slab path's own passes when the library reports slabs."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    st = dict(n_splats=1000, n_sorted=800, n_visible=600, n_tile_instances=5000, n_tiles=100, width=160, height=160,
+              n_slabs=0, n_slabs_run=0, n_slab_entries=0, n_instances_kept=900)
+    ab = bench.algorithmic_bytes(st)
+    assert ab["sort"] == 20 * 1000 + 8 * 800 and ab["raster"] == 36 * 5000 + 4 * 160 * 160
+    assert ab["total"] == ab["sort"] + ab["project"] + ab["bin"] + ab["raster"]
+    st.update(n_slabs=3, n_slabs_run=2, n_slab_entries=700)
+    sb = bench.algorithmic_bytes(st)
+    assert sb["sort"] == 36 * 1000 and sb["project"] == 0
+    assert sb["bin"] == 2 * 4 * 1000 + 700 * 86 + 80 * 900 + 8 * 100 * 2
+    assert sb["total"] == sb["sort"] + sb["bin"] + sb["raster"]
