@@ -5,9 +5,12 @@
 //                32 B projected record per splat + its packed tile rectangle.
 //   k_count    : per entry of the draw order (== reference sortedIndexes): instance offset inside its 256-entry slice;
 //                per slice: total; last CTA: prefix over the slices + frame total D.
-//   k_emit     : one CTA per window of 2048 instance positions -> writes (tile, splat) instances in draw order, so
-//                that a STABLE sort by tile id alone reproduces the reference's back-to-front order inside every tile.
-//                k_emit also produces pass T1's per-window digit histograms (table[digit][window]).
+//                Sparse frames (fewer than half of the splats sorted): each chunk's survivors are compacted first.
+//   k_emit_entries (default): one thread per draw-order entry writes its (bin, splat) instances at the entry's offset,
+//                in draw order, so that a STABLE sort by bin id alone reproduces the reference's back-to-front order
+//                inside every bin; rectangles of more than 8 bins are finished by the whole warp.
+//   k_emit     (GS_EMIT=windows, round 1): one CTA per window of 2048 instance positions; also produces pass T1's
+//                per-window digit histograms (table[digit][window]).
 #include "gs_common.cuh"
 
 namespace gs {

@@ -4,8 +4,10 @@
 //   k_depth_cull  : index.js:517-555  depth (fp64, left to right), cutout box, filter, min/max
 //   k_radix_{hist,scan,scatter}<D1/D2>: index.js:557-567  16-bit key = ToInt32((f32 depth - min) * depthInv), stable
 //                   counting sort as two 8-bit passes
-//   k_radix_{scan,scatter}<T1>, k_radix_{hist,scan,scatter}<T2>: stable sort of tile instances by 16-bit tile id
-//                   (T1's histograms come from k_emit; T2 also gathers the 32 B records)
+//   k_radix_{hist,scan,scatter}<T1>, <T2>: stable sort of bin instances by 16-bit bin id; the final pass (T1 when a
+//                   frame has at most 256 bins, else T2) also gathers the 32 B records (with GS_EMIT=windows T1's
+//                   histograms come from k_emit instead of k_radix_hist<T1>)
+//   k_radix_{hist,scan,scatter}<S1>: first pass of a depth slab's sort (keys from the slab's compacted entries)
 //   k_tile_ranges : per-bin {start, end} in the final instance order (frames of more than 256 bins; otherwise pass T1 writes them)
 //
 // Bit-exactness: JS evaluates in fp64 with IEEE rounding after every operation; the kernels use
